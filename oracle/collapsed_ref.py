@@ -1,0 +1,170 @@
+"""ORACLE (test infrastructure only) -- the collapsed score network + hand reverse mode.
+
+This is the formulation the CUDA kernel executes, written
+with dense torch ops on the CPU in any dtype (fp64 for validation).  It is checked
+against `score_ref.score_forward` (the literal restatement, autograd forces) and
+against the reference's own outputs in tests/golden.
+
+Intrinsic-coordinate mode (`use_intrinsic_coords=True, use_abs_coords=False,
+use_distances=False, conservative=True` -- every shipped checkpoint):
+
+  e_ij = W_ekv (W_e (x_j - x_i) + b_e) + b_ekv = A (x_j - x_i) + c   (graph_transformer.py:96, :235;
+                                                                      norm_edges is Identity, :288)
+  sim_ij^h = s q_i^h . (k_j^h + e_ij^h)  ->  softmax_j of  s (q_i^h . k_j^h + u_i^h . x_j),  u_i^h = A_h^T q_i^h
+  o_i^h   = sum_j p_ij (v_j^h + e_ij^h) = sum_j p_ij v_j^h + A_h (xbar_i^h - x_i) + c_h
+
+`forward_backward` returns forces = -d(sum E)/dx plus (optionally) every
+intermediate the kernel stashes, keyed like the kernel's scratch regions.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+
+from .score_ref import DIM_HEAD, HEADS, LN_EPS, num_layers
+
+INNER = HEADS * DIM_HEAD
+SCALE = DIM_HEAD ** -0.5
+
+
+def fold_edge_path(p: Dict[str, torch.Tensor], l: int):
+    """A = W_ekv W_e  [512,E],  c = W_ekv b_e + b_ekv  [512]  (computed in fp64, cast back)."""
+    pre = f"graphtransformer.layers.{l}.0.0.fn."
+    Wekv = p[pre + "edges_to_kv.weight"].double()
+    A = Wekv @ p["edge_embedding.weight"].double()
+    c = Wekv @ p["edge_embedding.bias"].double() + p[pre + "edges_to_kv.bias"].double()
+    dt = p["edge_embedding.weight"].dtype
+    return A.to(dt), c.to(dt)
+
+
+def _ln_fwd(x, g, b):
+    mu = x.mean(-1, keepdim=True)
+    var = ((x - mu) ** 2).mean(-1, keepdim=True)
+    rstd = torch.rsqrt(var + LN_EPS)
+    y = (x - mu) * rstd
+    return y * g + b, y, rstd
+
+
+def _ln_bwd(dout, y, rstd, g):
+    dy = dout * g
+    return rstd * (dy - dy.mean(-1, keepdim=True) - y * (dy * y).mean(-1, keepdim=True))
+
+
+def _gate_fwd(w, a, n):
+    H = a.shape[-1]
+    wa, wb, wc = w[0, :H], w[0, H:2 * H], w[0, 2 * H:]
+    z = (a * (wa + wc)).sum(-1, keepdim=True) + (n * (wb - wc)).sum(-1, keepdim=True)
+    g = torch.sigmoid(z)
+    return a * g + n * (1 - g), g
+
+
+def _gate_bwd(w, a, n, g, dout):
+    H = a.shape[-1]
+    wa, wb, wc = w[0, :H], w[0, H:2 * H], w[0, 2 * H:]
+    dg = (dout * (a - n)).sum(-1, keepdim=True)
+    dz = dg * g * (1 - g)
+    da = dout * g + dz * (wa + wc)
+    dn = dout * (1 - g) + dz * (wb - wc)
+    return da, dn
+
+
+def _gelu(x):
+    return 0.5 * x * (1 + torch.erf(x / math.sqrt(2.0)))
+
+
+def _gelu_grad(x):
+    return 0.5 * (1 + torch.erf(x / math.sqrt(2.0))) + x * torch.exp(-0.5 * x * x) / math.sqrt(2 * math.pi)
+
+
+def _heads(t):          # [B,N,512] -> [B,8,N,64]
+    B, N, _ = t.shape
+    return t.reshape(B, N, HEADS, DIM_HEAD).permute(0, 2, 1, 3)
+
+
+def _unheads(t):        # [B,8,N,64] -> [B,N,512]
+    B, _, N, _ = t.shape
+    return t.permute(0, 2, 1, 3).reshape(B, N, INNER)
+
+
+def node_embedding0(p, N: int, t_norm: float, dtype):
+    """Layer-0 node stream: W_n [onehot_i, t] + b_n  -- independent of x and of the sample
+    (graph_transformer.py:99-103 with h = eye(N))."""
+    Wn = p["node_embedding.weight"].to(dtype)
+    return Wn[:, :N].t() + Wn[:, N] * t_norm + p["node_embedding.bias"].to(dtype)     # [N,H]
+
+
+def forward_backward(p: Dict[str, torch.Tensor], x: torch.Tensor, t_norm: float,
+                     want_stash: bool = False):
+    """x [B,N,3] (any float dtype; centred internally), t_norm python float.
+    Returns (forces [B,N,3], energy [B,N], stash or None)."""
+    dtype = x.dtype
+    p = {k: v.to(dtype) for k, v in p.items()}
+    x = x - x.mean(dim=1, keepdim=True)
+    B, N, _ = x.shape
+    L = num_layers(p)
+    H = p["node_embedding.weight"].shape[0]
+    nodes = node_embedding0(p, N, float(t_norm), dtype).unsqueeze(0).expand(B, N, H)
+    saved = []
+    for l in range(L):
+        a_ = f"graphtransformer.layers.{l}.0."
+        f_ = f"graphtransformer.layers.{l}.1."
+        A, c = fold_edge_path(p, l)
+        Ah = A.reshape(HEADS, DIM_HEAD, 3)
+        ch = c.reshape(HEADS, DIM_HEAD)
+        n_in = nodes
+        nh, y1, r1 = _ln_fwd(n_in, p[a_ + "0.norm.weight"], p[a_ + "0.norm.bias"])
+        q = nh @ p[a_ + "0.fn.to_q.weight"].t() + p[a_ + "0.fn.to_q.bias"]
+        kv = nh @ p[a_ + "0.fn.to_kv.weight"].t() + p[a_ + "0.fn.to_kv.bias"]
+        k, v = kv[..., :INNER], kv[..., INNER:]
+        qh, kh, vh = _heads(q), _heads(k), _heads(v)
+        u = torch.einsum("bhid,hdc->bhic", qh, Ah)                          # [B,8,N,3]
+        logits = SCALE * (qh @ kh.transpose(-1, -2) + torch.einsum("bhic,bjc->bhij", u, x))
+        pr = logits.softmax(-1)                                             # [B,8,N,N]
+        xbar = torch.einsum("bhij,bjc->bhic", pr, x)
+        oh = pr @ vh + torch.einsum("hdc,bhic->bhid", Ah, xbar - x[:, None]) + ch[None, :, None, :]
+        att = _unheads(oh) @ p[a_ + "0.fn.to_out.weight"].t() + p[a_ + "0.fn.to_out.bias"]
+        m, g1 = _gate_fwd(p[a_ + "1.proj.0.weight"], att, n_in)
+        mh, y2, r2 = _ln_fwd(m, p[f_ + "0.norm.weight"], p[f_ + "0.norm.bias"])
+        h1 = mh @ p[f_ + "0.fn.0.weight"].t() + p[f_ + "0.fn.0.bias"]
+        ff = _gelu(h1) @ p[f_ + "0.fn.2.weight"].t() + p[f_ + "0.fn.2.bias"]
+        nodes, g2 = _gate_fwd(p[f_ + "1.proj.0.weight"], ff, m)
+        saved.append(dict(n_in=n_in, y1=y1, r1=r1, q=q, k=k, v=v, u=u, p=pr, att=att, g1=g1, m=m,
+                          y2=y2, r2=r2, h1=h1, ff=ff, g2=g2, Ah=Ah, out=nodes))
+    wd = p["node_decoder.weight"][0]
+    energy = nodes @ wd + p["node_decoder.bias"][0]                          # [B,N]
+
+    # ---- reverse mode w.r.t. x (d sum(E)) ----
+    dn = wd.expand(B, N, H).clone()
+    dx = torch.zeros_like(x)
+    for l in reversed(range(L)):
+        a_ = f"graphtransformer.layers.{l}.0."
+        f_ = f"graphtransformer.layers.{l}.1."
+        s = saved[l]
+        Ah = s["Ah"]
+        dff, dm = _gate_bwd(p[f_ + "1.proj.0.weight"], s["ff"], s["m"], s["g2"], dn)
+        dact = dff @ p[f_ + "0.fn.2.weight"]
+        dh1 = dact * _gelu_grad(s["h1"])
+        dmh = dh1 @ p[f_ + "0.fn.0.weight"]
+        dm = dm + _ln_bwd(dmh, s["y2"], s["r2"], p[f_ + "0.norm.weight"])
+        datt, dn_res = _gate_bwd(p[a_ + "1.proj.0.weight"], s["att"], s["n_in"], s["g1"], dm)
+        do = _heads(datt @ p[a_ + "0.fn.to_out.weight"])                    # [B,8,N,64]
+        qh, kh, vh = _heads(s["q"]), _heads(s["k"]), _heads(s["v"])
+        w = torch.einsum("bhid,hdc->bhic", do, Ah)                          # [B,8,N,3]
+        dp = do @ vh.transpose(-1, -2) + torch.einsum("bhic,bjc->bhij", w, x)
+        ds = s["p"] * (dp - (s["p"] * dp).sum(-1, keepdim=True))
+        dx = dx + torch.einsum("bhij,bhic->bjc", s["p"], w) \
+                + SCALE * torch.einsum("bhij,bhic->bjc", ds, s["u"]) - w.sum(1)
+        if l == 0:
+            s["do"], s["ds"], s["w"] = do, ds, w
+            break                                                           # layer-0 nodes do not depend on x
+        dsx = torch.einsum("bhij,bjc->bhic", ds, x)
+        dq = SCALE * (ds @ kh + torch.einsum("hdc,bhic->bhid", Ah, dsx))
+        dk = SCALE * (ds.transpose(-1, -2) @ qh)
+        dv = s["p"].transpose(-1, -2) @ do
+        dnh = _unheads(dq) @ p[a_ + "0.fn.to_q.weight"] \
+            + torch.cat([_unheads(dk), _unheads(dv)], -1) @ p[a_ + "0.fn.to_kv.weight"]
+        dn = dn_res + _ln_bwd(dnh, s["y1"], s["r1"], p[a_ + "0.norm.weight"])
+        s["do"], s["ds"], s["w"], s["dq"], s["dk"], s["dv"], s["dn_in"] = do, ds, w, dq, dk, dv, dn
+    return -dx, energy, (saved if want_stash else None)

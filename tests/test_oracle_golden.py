@@ -1,0 +1,93 @@
+"""CPU: pin the oracle against outputs of the unmodified reference (tests/golden, made by oracle/make_golden.py)."""
+import pytest
+import torch
+
+from helpers import FORCE_RTOL, MOLS, load, net_params, rel_err, schedule
+from oracle import collapsed_ref, sampler_ref, score_ref
+from oracle.weights import synthetic_net_params
+
+
+@pytest.mark.parametrize("mol", MOLS)
+def test_literal_score_matches_reference(mol):
+    p = net_params(mol)
+    for c in load(f"score_{mol}.pt")["cases"]:
+        f = score_ref.score_forward(p, c["x"], c["t_norm"])
+        e = score_ref.score_forward(p, c["x"], c["t_norm"], return_energy=True)[..., 0]
+        # same ops, same order, same library -> expect (near) bit equality
+        assert rel_err(f, c["forces"]) < 2e-6, (mol, c["t"])
+        assert rel_err(e, c["energy"]) < 2e-6, (mol, c["t"])
+
+
+@pytest.mark.parametrize("mol", MOLS)
+def test_collapsed_fp64_matches_reference(mol):
+    p = net_params(mol)
+    for c in load(f"score_{mol}.pt")["cases"][:3]:
+        f, e, _ = collapsed_ref.forward_backward(score_ref.to_dtype(p, torch.float64), c["x"].double(), c["t_norm"])
+        # reference is fp32: its own fp32-vs-fp64 gap is 2e-6..1e-5
+        assert rel_err(f, c["forces"]) < 5e-5, (mol, c["t"], rel_err(f, c["forces"]))
+        assert rel_err(e, c["energy"]) < 5e-5, (mol, c["t"])
+
+
+def test_collapsed_equals_literal_fp64():
+    p = score_ref.to_dtype(synthetic_net_params(9, 64, 2, seed=11), torch.float64)
+    x = torch.randn(3, 9, 3, dtype=torch.float64, generator=torch.Generator().manual_seed(3))
+    f_lit = score_ref.score_forward(p, x, 0.3)
+    e_lit = score_ref.score_forward(p, x, 0.3, return_energy=True)[..., 0]
+    f_col, e_col, _ = collapsed_ref.forward_backward(p, x, 0.3)
+    assert rel_err(f_col, f_lit) < 1e-11
+    assert rel_err(e_col, e_lit) < 1e-11
+
+
+def test_synthetic_weights_through_reference():
+    g = load("score_synth.pt")
+    for key, c in g.items():
+        p = synthetic_net_params(c["N"], c["H"], c["L"], c["seed"])
+        f = score_ref.score_forward(p, c["x"], c["t_norm"])
+        assert rel_err(f, c["forces"]) < 2e-6, key
+        f64, _, _ = collapsed_ref.forward_backward(score_ref.to_dtype(p, torch.float64), c["x"].double(), c["t_norm"])
+        assert rel_err(f64, c["forces"]) < 5e-5, key
+
+
+@pytest.mark.parametrize("mol", MOLS)
+def test_schedule_buffers(mol):
+    ck = schedule(mol)
+    mine = sampler_ref.cosine_schedule(1000)
+    for k in sampler_ref.SCHEDULE_KEYS:
+        assert torch.equal(mine[k], ck[k]) or rel_err(mine[k], ck[k]) < 1e-6, k
+
+
+@pytest.mark.parametrize("mol", ("chignolin", "ala2_fold1", "trp_cage"))
+def test_ddpm_chain(mol):
+    p, sched = net_params(mol), schedule(mol)
+    score = lambda x, tn: score_ref.score_forward(p, x, tn)
+    for ch in load(f"ddpm_{mol}.pt")["chains"]:
+        x = ch["x_init"]
+        for s in range(ch["steps"]):
+            x = sampler_ref.ddpm_step(score, sched, x, ch["t_start"] - s, 1000, ch["noise"][s])
+            assert rel_err(x, ch["x_steps"][s]) < 1e-5, (mol, ch["t_start"], s)
+
+
+@pytest.mark.parametrize("mol", ("chignolin", "ala2_fold1", "trp_cage"))
+def test_langevin_runs(mol):
+    p, sched = net_params(mol), schedule(mol)
+    g = load(f"langevin_{mol}.pt")
+    std = g["meta"]["std"]
+    score = lambda x, tn: score_ref.score_forward(p, x, tn)
+    for r in g["runs"]:
+        c = sampler_ref.langevin_constants(sched, std, r["t"], r["temp"], r["temp"], r["masses"], r["friction"], None)
+        assert abs(c["dt"] - r["dt"]) <= 1e-12 * abs(r["dt"]) and abs(c["beta"] - r["beta"]) <= 1e-12 * r["beta"]
+        coords, ke, _, _ = sampler_ref.langevin_simulate(score, c, r["init_mol"] / std, r["masses"], r["friction"],
+                                                         r["t"], 1000, r["steps"], r["save_interval"], noise=r["noise"])
+        traj = (coords.permute(1, 0, 2, 3).reshape(-1, coords.shape[2], 3)) * std      # sim-major, langevin.py:209-211
+        assert rel_err(traj, r["traj"]) < 1e-5, (mol, r["friction"])
+        if r["kinetic"] is not None:
+            assert rel_err(ke.t(), r["kinetic"]) < 1e-4
+
+
+def test_ddpm_full_chain_ala2():
+    g = load("ddpm_full_ala2.pt")
+    p, sched = net_params("ala2_fold1"), schedule("ala2_fold1")
+    torch.set_rng_state(g["rng_state"])
+    score = lambda x, tn: score_ref.score_forward(p, x, tn)
+    x = sampler_ref.ddpm_sample_loop(score, sched, (2, 5, 3)) * g["meta"]["std"]
+    assert rel_err(x, g["sample"]) < 1e-3
