@@ -1,0 +1,478 @@
+// dff_b200.cu -- host side of libdff_b200.so: weight packing (K0), launch policy and the C ABI
+// declared in include/dff_b200.h.  No torch types here; PyTorch only lends device pointers.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/dff_b200.h"
+#include "dff_kernel.cuh"
+
+using namespace dff;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                        \
+    do {                                                                                      \
+        cudaError_t e_ = (expr);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(DFF_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct SegHost {
+    size_t offset;      // floats into the packed buffer
+    uint32_t slice_bytes, n_slices;
+};
+
+constexpr int ks_for(int nc) { return nc == 384 ? 8 : (nc == 192 ? 16 : (nc == 128 ? 16 : 32)); }
+
+}  // namespace
+
+struct dff_model {
+    int device = 0, num_sms = 0;
+    int N = 0, NP = 0, H = 0, HP = 0, L = 0, nch = 0;
+    int max_batch = 0;
+    float* d_weights = nullptr;     // every packed tensor + GEMM panel
+    Seg* d_segs = nullptr;
+    float* d_scratch = nullptr;
+    ModelDev md{};                  // template; S / stash geometry are filled per launch
+    int nseg_fwd = 0, nseg_all = 0;
+    uint32_t nslice_fwd = 0, nslice_all = 0;
+    long long layer_floats[2] = {0, 0};          // for R = 32, 64
+    long long off[2][ST_COUNT];
+    long long scratch_per_cta = 0;               // floats (sized for R = 64)
+    int64_t launches = 0;
+    // staging for the *_host entry points
+    float* d_io[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t d_io_cap[6] = {0, 0, 0, 0, 0, 0};
+    uint32_t* d_flags = nullptr;
+    float* d_sched = nullptr;  size_t d_sched_T = 0;
+    int last_R = 0, last_S = 0;
+};
+
+namespace {
+
+void stash_geometry(int R, int N_pad, int H, long long* off, long long* layer_floats) {
+    long long o = 0;
+    auto put = [&](int region, long long n) { off[region] = o; o += (n + 3) / 4 * 4; };
+    put(ST_NIN, (long long)R * H);
+    put(ST_STAT1, 2LL * R);
+    put(ST_QKV, 8LL * R * 192);
+    put(ST_P, 8LL * R * N_pad);
+    put(ST_ATT, (long long)R * H);
+    put(ST_G1, R);
+    put(ST_M, (long long)R * H);
+    put(ST_STAT2, 2LL * R);
+    put(ST_H1, 4LL * R * H);
+    put(ST_FF, (long long)R * H);
+    put(ST_G2, R);
+    *layer_floats = o;
+}
+
+struct Packer {
+    std::vector<float> buf;
+    size_t alloc(size_t n) {
+        size_t o = buf.size();
+        buf.resize(o + (n + 3) / 4 * 4, 0.f);
+        return o;
+    }
+};
+
+template <int HP, int R>
+int launch_cfg(dff_model* m, const ModelDev& M, const StepArgs& A, int grid, cudaStream_t stream) {
+    static bool attr_set[8] = {false};
+    auto kern = dff_fused_kernel<HP, R>;
+    const size_t smem = Cfg<HP, R>::kSmemBytes;
+    if (!attr_set[m->device & 7]) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[m->device & 7] = true;
+    }
+    kern<<<grid, kThreads, smem, stream>>>(M, A);
+    CUDA_TRY(cudaGetLastError());
+    m->launches += 1;
+    return DFF_OK;
+}
+
+int launch(dff_model* m, StepArgs& A, cudaStream_t stream) {
+    if (A.B <= 0) return DFF_OK;
+    if (A.B > m->max_batch) return fail(DFF_EINVAL, "batch %d exceeds max_batch %d given to dff_model_create", A.B, m->max_batch);
+    CUDA_TRY(cudaSetDevice(m->device));
+    const int N = m->N;
+    const int s64 = 64 / N, s32 = 32 / N;
+    const int need = (A.B + m->num_sms - 1) / m->num_sms;   // samples per CTA that cover the batch in one wave
+    int R, S;
+    if (s32 >= 1 && need <= s32) { R = 32; S = std::max(need, 1); }
+    else { R = 64; S = std::min(s64, std::max(need, 1)); }
+    const int ri = (R == 64) ? 1 : 0;
+    ModelDev M = m->md;
+    M.S = S;
+    M.layer_floats = m->layer_floats[ri];
+    for (int i = 0; i < ST_COUNT; ++i) M.off[i] = m->off[ri][i];
+    const int n_groups = (A.B + S - 1) / S;
+    const int grid = std::min(n_groups, m->num_sms);
+    m->last_R = R; m->last_S = S;
+    if (m->HP == 64) return (R == 64) ? launch_cfg<64, 64>(m, M, A, grid, stream) : launch_cfg<64, 32>(m, M, A, grid, stream);
+    return (R == 64) ? launch_cfg<128, 64>(m, M, A, grid, stream) : launch_cfg<128, 32>(m, M, A, grid, stream);
+}
+
+int ensure_io(dff_model* m, int slot, size_t floats) {
+    if (m->d_io_cap[slot] >= floats) return DFF_OK;
+    if (m->d_io[slot]) cudaFree(m->d_io[slot]);
+    m->d_io[slot] = nullptr; m->d_io_cap[slot] = 0;
+    CUDA_TRY(cudaMalloc(&m->d_io[slot], floats * sizeof(float)));
+    m->d_io_cap[slot] = floats;
+    return DFF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* dff_last_error(void) { return g_err.c_str(); }
+int dff_version(void) { return 100; }
+int dff_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int dff_model_create(dff_model_t** out, int device, int num_beads, int hidden, int n_layers,
+                     const float* const* w, int n_weights, int max_batch) {
+    if (!out) return fail(DFF_EINVAL, "out is NULL");
+    *out = nullptr;
+    const int N = num_beads, H = hidden, L = n_layers;
+    if (N < 2 || N > kMaxBeads) return fail(DFF_EINVAL, "num_beads %d unsupported (2..%d)", N, kMaxBeads);
+    if (H < 32 || H > 128 || H % 32) return fail(DFF_EINVAL, "hidden %d unsupported (32, 64, 96, 128)", H);
+    if (L < 1 || L > kMaxLayers) return fail(DFF_EINVAL, "n_layers %d unsupported (1..%d)", L, kMaxLayers);
+    if (n_weights != DFF_NUM_GLOBAL_WEIGHTS + DFF_NUM_LAYER_WEIGHTS * L)
+        return fail(DFF_EINVAL, "expected %d weight tensors, got %d", DFF_NUM_GLOBAL_WEIGHTS + DFF_NUM_LAYER_WEIGHTS * L, n_weights);
+    for (int i = 0; i < n_weights; ++i)
+        if (!w[i]) return fail(DFF_EINVAL, "weight pointer %d is NULL", i);
+    if (max_batch < 1) return fail(DFF_EINVAL, "max_batch must be >= 1");
+    int ndev = dff_device_count();
+    if (ndev <= 0) return fail(DFF_ENODEV, "no CUDA device visible: this library has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(DFF_EINVAL, "device %d out of range (%d visible)", device, ndev);
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(DFF_ENODEV, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+
+    dff_model* m = new dff_model();
+    m->device = device; m->num_sms = prop.multiProcessorCount;
+    m->N = N; m->NP = (N + 3) / 4 * 4; m->H = H; m->HP = (H <= 64) ? 64 : 128; m->L = L; m->nch = 4 * H / 128;
+    m->max_batch = max_batch;
+    const int HP = m->HP, nch = m->nch;
+    if ((4 * H) % 128) { delete m; return fail(DFF_EINVAL, "4*hidden must be a multiple of 128"); }
+
+    const float* Wn = w[0]; const float* bn = w[1]; const float* We = w[2]; const float* be = w[3];
+    const float* Wd = w[4]; const float* bd = w[5];
+
+    Packer P;
+    struct LayerOff { size_t ln1_g, ln1_b, bqkv, A, cvec, bo, g1a, g1b, ln2_g, ln2_b, b1, b2, g2a, g2b; };
+    std::vector<LayerOff> lo(L);
+    const size_t o_emb = P.alloc((size_t)N * H), o_embt = P.alloc(H), o_dec = P.alloc(H);
+    for (int i = 0; i < N; ++i)
+        for (int d = 0; d < H; ++d) P.buf[o_emb + (size_t)i * H + d] = Wn[(size_t)d * (N + 1) + i] + bn[d];
+    for (int d = 0; d < H; ++d) { P.buf[o_embt + d] = Wn[(size_t)d * (N + 1) + N]; P.buf[o_dec + d] = Wd[d]; }
+
+    auto LW = [&](int l, int k) { return w[DFF_NUM_GLOBAL_WEIGHTS + DFF_NUM_LAYER_WEIGHTS * l + k]; };
+    for (int l = 0; l < L; ++l) {
+        LayerOff& o = lo[l];
+        const float *ln1g = LW(l, 0), *ln1b = LW(l, 1), *bq = LW(l, 3), *bkv = LW(l, 5), *Wekv = LW(l, 6), *bekv = LW(l, 7),
+                    *bo = LW(l, 9), *g1 = LW(l, 10), *ln2g = LW(l, 11), *ln2b = LW(l, 12), *b1 = LW(l, 14), *b2 = LW(l, 16),
+                    *g2 = LW(l, 17);
+        o.ln1_g = P.alloc(H); o.ln1_b = P.alloc(H); o.bqkv = P.alloc(8 * 192); o.A = P.alloc(512 * 4); o.cvec = P.alloc(512);
+        o.bo = P.alloc(HP); o.g1a = P.alloc(H); o.g1b = P.alloc(H); o.ln2_g = P.alloc(H); o.ln2_b = P.alloc(H);
+        o.b1 = P.alloc(4 * H); o.b2 = P.alloc(HP); o.g2a = P.alloc(H); o.g2b = P.alloc(H);
+        for (int d = 0; d < H; ++d) {
+            P.buf[o.ln1_g + d] = ln1g[d]; P.buf[o.ln1_b + d] = ln1b[d];
+            P.buf[o.ln2_g + d] = ln2g[d]; P.buf[o.ln2_b + d] = ln2b[d];
+            P.buf[o.bo + d] = bo[d]; P.buf[o.b2 + d] = b2[d];
+            P.buf[o.g1a + d] = g1[d] + g1[2 * H + d]; P.buf[o.g1b + d] = g1[H + d] - g1[2 * H + d];
+            P.buf[o.g2a + d] = g2[d] + g2[2 * H + d]; P.buf[o.g2b + d] = g2[H + d] - g2[2 * H + d];
+        }
+        for (int j = 0; j < 4 * H; ++j) P.buf[o.b1 + j] = b1[j];
+        for (int h = 0; h < 8; ++h)
+            for (int j = 0; j < 64; ++j) {
+                P.buf[o.bqkv + h * 192 + j] = bq[h * 64 + j];
+                P.buf[o.bqkv + h * 192 + 64 + j] = bkv[h * 64 + j];
+                P.buf[o.bqkv + h * 192 + 128 + j] = bkv[512 + h * 64 + j];
+            }
+        // fold edge_embedding into edges_to_kv (exact: no nonlinearity between them, graph_transformer.py:96,235,288)
+        for (int j = 0; j < 512; ++j) {
+            double a[3] = {0, 0, 0}, cc = bekv[j];
+            for (int k = 0; k < H; ++k) {
+                const double wk = Wekv[(size_t)j * H + k];
+                a[0] += wk * We[k * 3 + 0]; a[1] += wk * We[k * 3 + 1]; a[2] += wk * We[k * 3 + 2];
+                cc += wk * be[k];
+            }
+            P.buf[o.A + j * 4 + 0] = (float)a[0]; P.buf[o.A + j * 4 + 1] = (float)a[1]; P.buf[o.A + j * 4 + 2] = (float)a[2];
+            P.buf[o.cvec + j] = (float)cc;
+        }
+    }
+
+    // GEMM panels [K][NC] in the exact order the kernel consumes them
+    std::vector<SegHost> segs;
+    auto panel = [&](int K, int NC, auto&& fill /* (k, c) -> value */) {
+        const size_t o = P.alloc((size_t)K * NC);
+        for (int k = 0; k < K; ++k)
+            for (int c2 = 0; c2 < NC; ++c2) P.buf[o + (size_t)k * NC + c2] = fill(k, c2);
+        const int KS = ks_for(NC);
+        segs.push_back({o, (uint32_t)(KS * NC * sizeof(float)), (uint32_t)(K / KS)});
+    };
+    for (int l = 0; l < L; ++l) {
+        const float *Wq = LW(l, 2), *Wkv = LW(l, 4), *Wo = LW(l, 8), *W1 = LW(l, 13), *W2 = LW(l, 15);
+        for (int h = 0; h < 8; ++h) {
+            panel(H, 192, [&](int k, int c2) {
+                const int t = c2 / 64, j = c2 % 64;
+                return t == 0 ? Wq[(size_t)(h * 64 + j) * H + k]
+                              : Wkv[(size_t)((t == 1 ? 0 : 512) + h * 64 + j) * H + k];
+            });
+            panel(64, HP, [&](int k, int d) { return d < H ? Wo[(size_t)d * 512 + h * 64 + k] : 0.f; });
+        }
+        for (int ch = 0; ch < nch; ++ch) {
+            panel(H, 128, [&](int k, int j) { return W1[(size_t)(ch * 128 + j) * H + k]; });
+            panel(128, HP, [&](int k, int d) { return d < H ? W2[(size_t)d * 4 * H + ch * 128 + k] : 0.f; });
+        }
+    }
+    m->nseg_fwd = (int)segs.size();
+    for (int l = L - 1; l >= 0; --l) {
+        const float *Wq = LW(l, 2), *Wkv = LW(l, 4), *Wo = LW(l, 8), *W1 = LW(l, 13), *W2 = LW(l, 15);
+        for (int ch = 0; ch < nch; ++ch) {
+            panel(H, 128, [&](int d, int j) { return W2[(size_t)d * 4 * H + ch * 128 + j]; });
+            panel(128, HP, [&](int j, int d) { return d < H ? W1[(size_t)(ch * 128 + j) * H + d] : 0.f; });
+        }
+        for (int h = 0; h < 8; ++h) {
+            panel(H, 64, [&](int d, int j) { return Wo[(size_t)d * 512 + h * 64 + j]; });
+            if (l > 0)
+                panel(192, HP, [&](int k, int d) {   // rows: dv' | dk' | dq
+                    if (d >= H) return 0.f;
+                    const int t = k / 64, j = k % 64;
+                    return t == 0 ? Wkv[(size_t)(512 + h * 64 + j) * H + d]
+                         : t == 1 ? Wkv[(size_t)(h * 64 + j) * H + d]
+                                  : Wq[(size_t)(h * 64 + j) * H + d];
+                });
+        }
+    }
+    m->nseg_all = (int)segs.size();
+    for (int i = 0; i < m->nseg_all; ++i) {
+        if (i < m->nseg_fwd) m->nslice_fwd += segs[i].n_slices;
+        m->nslice_all += segs[i].n_slices;
+    }
+
+    auto cleanup = [&]() { dff_model_destroy(m); };
+    if (cudaMalloc(&m->d_weights, P.buf.size() * sizeof(float)) != cudaSuccess) { cleanup(); return fail(DFF_ENOMEM, "cudaMalloc weights failed"); }
+    if (cudaMemcpy(m->d_weights, P.buf.data(), P.buf.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) { cleanup(); return fail(DFF_ECUDA, "weight upload failed"); }
+    std::vector<Seg> hs(segs.size());
+    for (size_t i = 0; i < segs.size(); ++i) hs[i] = Seg{m->d_weights + segs[i].offset, segs[i].slice_bytes, segs[i].n_slices};
+    if (cudaMalloc(&m->d_segs, hs.size() * sizeof(Seg)) != cudaSuccess) { cleanup(); return fail(DFF_ENOMEM, "cudaMalloc segs failed"); }
+    if (cudaMemcpy(m->d_segs, hs.data(), hs.size() * sizeof(Seg), cudaMemcpyHostToDevice) != cudaSuccess) { cleanup(); return fail(DFF_ECUDA, "segment upload failed"); }
+
+    stash_geometry(32, m->NP, H, m->off[0], &m->layer_floats[0]);
+    stash_geometry(64, m->NP, H, m->off[1], &m->layer_floats[1]);
+    m->scratch_per_cta = (long long)L * m->layer_floats[1] + 64LL * H;
+    const int s_max = std::max(1, 64 / N);
+    const int n_ctas = std::min(m->num_sms, std::max(1, max_batch));
+    (void)s_max;
+    if (cudaMalloc(&m->d_scratch, (size_t)n_ctas * m->scratch_per_cta * sizeof(float)) != cudaSuccess) { cleanup(); return fail(DFF_ENOMEM, "cudaMalloc scratch failed"); }
+    if (cudaMalloc(&m->d_flags, sizeof(uint32_t)) != cudaSuccess) { cleanup(); return fail(DFF_ENOMEM, "cudaMalloc flags failed"); }
+
+    ModelDev& M = m->md;
+    M.N = N; M.NP = m->NP; M.H = H; M.L = L; M.S = 1; M.nch = nch;
+    M.emb = m->d_weights + o_emb; M.embt = m->d_weights + o_embt; M.dec_w = m->d_weights + o_dec; M.dec_b = bd[0];
+    for (int l = 0; l < L; ++l) {
+        const LayerOff& o = lo[l];
+        LayerDev& D = M.layer[l];
+        const float* b = m->d_weights;
+        D.ln1_g = b + o.ln1_g; D.ln1_b = b + o.ln1_b; D.bqkv = b + o.bqkv; D.A = b + o.A; D.cvec = b + o.cvec; D.bo = b + o.bo;
+        D.g1a = b + o.g1a; D.g1b = b + o.g1b; D.ln2_g = b + o.ln2_g; D.ln2_b = b + o.ln2_b; D.b1 = b + o.b1; D.b2 = b + o.b2;
+        D.g2a = b + o.g2a; D.g2b = b + o.g2b;
+    }
+    M.segs = m->d_segs; M.nseg_fwd = m->nseg_fwd; M.nseg_all = m->nseg_all;
+    M.nslice_fwd = m->nslice_fwd; M.nslice_all = m->nslice_all;
+    M.scratch = m->d_scratch; M.scratch_per_cta = m->scratch_per_cta;
+    *out = m;
+    return DFF_OK;
+}
+
+void dff_model_destroy(dff_model_t* m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    if (m->d_weights) cudaFree(m->d_weights);
+    if (m->d_segs) cudaFree(m->d_segs);
+    if (m->d_scratch) cudaFree(m->d_scratch);
+    if (m->d_flags) cudaFree(m->d_flags);
+    if (m->d_sched) cudaFree(m->d_sched);
+    for (auto p : m->d_io) if (p) cudaFree(p);
+    delete m;
+}
+
+int dff_model_num_beads(const dff_model_t* m) { return m ? m->N : 0; }
+int dff_model_hidden(const dff_model_t* m) { return m ? m->H : 0; }
+int dff_model_layers(const dff_model_t* m) { return m ? m->L : 0; }
+int dff_model_device(const dff_model_t* m) { return m ? m->device : -1; }
+int64_t dff_model_launch_count(const dff_model_t* m) { return m ? m->launches : 0; }
+
+double dff_model_flops_per_sample(const dff_model_t* m) {
+    if (!m) return 0;
+    const double N = m->N, H = m->H, L = m->L, I = 512;
+    const double per_layer = 2 * N * H * 3 * I + 2 * (2 * N * I * 3) + 2 * 2 * N * N * (I + 24) + 2 * N * I * H + 16 * N * H * H + 12 * N * H;
+    const double fwd = L * per_layer + 2 * N * H;
+    return fwd + (fwd - 2 * N * H * 3 * I);
+}
+
+int dff_score_dev(dff_model_t* m, const float* x_dev, float t_norm, int batch, float* eps_out_dev,
+                  float* energy_out_dev, void* stream) {
+    if (!m || !x_dev) return fail(DFF_EINVAL, "NULL model or x");
+    StepArgs A{};
+    A.mode = MODE_SCORE; A.B = batch; A.n_steps = 1; A.need_backward = eps_out_dev != nullptr;
+    A.x = const_cast<float*>(x_dev); A.eps_out = eps_out_dev; A.energy_out = energy_out_dev; A.t_norm = t_norm;
+    return launch(m, A, (cudaStream_t)stream);
+}
+
+int dff_score_host(dff_model_t* m, const float* x_host, float t_norm, int batch, float* eps_out_host,
+                   float* energy_out_host) {
+    if (!m || !x_host) return fail(DFF_EINVAL, "NULL model or x");
+    CUDA_TRY(cudaSetDevice(m->device));
+    const size_t n = (size_t)batch * m->N;
+    int rc;
+    if ((rc = ensure_io(m, 0, n * 3)) || (rc = ensure_io(m, 1, n * 3)) || (rc = ensure_io(m, 2, n))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(m->d_io[0], x_host, n * 3 * sizeof(float), cudaMemcpyHostToDevice, 0));
+    rc = dff_score_dev(m, m->d_io[0], t_norm, batch, eps_out_host ? m->d_io[1] : nullptr, energy_out_host ? m->d_io[2] : nullptr, nullptr);
+    if (rc) return rc;
+    if (eps_out_host) CUDA_TRY(cudaMemcpyAsync(eps_out_host, m->d_io[1], n * 3 * sizeof(float), cudaMemcpyDeviceToHost, 0));
+    if (energy_out_host) CUDA_TRY(cudaMemcpyAsync(energy_out_host, m->d_io[2], n * sizeof(float), cudaMemcpyDeviceToHost, 0));
+    CUDA_TRY(cudaStreamSynchronize(0));
+    return DFF_OK;
+}
+
+int dff_ddpm_steps_dev(dff_model_t* m, float* x_dev, int batch, int t_start, int n_steps, int T,
+                       const float* const* sched_dev, const float* noise_dev, uint64_t seed, uint64_t offset,
+                       uint32_t* flags_dev, void* stream) {
+    if (!m || !x_dev || !sched_dev) return fail(DFF_EINVAL, "NULL argument");
+    if (n_steps < 0 || t_start >= T || t_start - n_steps + 1 < 0)
+        return fail(DFF_EINVAL, "timestep range [%d..%d] outside schedule of length %d", t_start - n_steps + 1, t_start, T);
+    if (n_steps == 0) return DFF_OK;
+    StepArgs A{};
+    A.mode = MODE_DDPM; A.B = batch; A.n_steps = n_steps; A.need_backward = 1;
+    A.x = x_dev; A.noise = noise_dev; A.t_start = t_start; A.T = T;
+    for (int i = 0; i < 5; ++i) { if (!sched_dev[i]) return fail(DFF_EINVAL, "schedule pointer %d is NULL", i); A.sched[i] = sched_dev[i]; }
+    A.seed = seed; A.offset = offset; A.flags = flags_dev;
+    return launch(m, A, (cudaStream_t)stream);
+}
+
+int dff_langevin_steps_dev(dff_model_t* m, float* x_dev, float* v_dev, int batch, int n_steps,
+                           const dff_md_params_t* p, const float* mass_dev, const float* noise_dev, uint64_t seed,
+                           uint64_t offset, int save_interval, float* frames_dev, float* ke_dev, uint32_t* flags_dev,
+                           void* stream) {
+    if (!m || !x_dev || !p) return fail(DFF_EINVAL, "NULL argument");
+    if (p->integrator == DFF_MD_BAOAB && (!v_dev || !mass_dev)) return fail(DFF_EINVAL, "BAOAB needs velocities and masses");
+    if (p->integrator != DFF_MD_BAOAB && p->integrator != DFF_MD_BROWNIAN) return fail(DFF_EINVAL, "unknown integrator %d", p->integrator);
+    if (save_interval > 0 && n_steps % save_interval) return fail(DFF_EINVAL, "save_interval must divide n_steps (langevin_cgnet.py:306-309)");
+    if (n_steps <= 0) return DFF_OK;
+    StepArgs A{};
+    A.mode = p->integrator == DFF_MD_BAOAB ? MODE_BAOAB : MODE_BROWNIAN;
+    A.B = batch; A.n_steps = n_steps; A.need_backward = 1;
+    A.x = x_dev; A.v = (A.mode == MODE_BAOAB) ? v_dev : nullptr; A.noise = noise_dev;
+    A.t_norm = p->t_norm; A.force_scale = p->force_scale; A.dt = p->dt; A.vscale = p->vscale; A.noisescale = p->noisescale;
+    A.inv_beta = (float)(1.0 / (double)p->beta); A.dtau = p->dtau;
+    A.bd_sigma = (float)sqrt(2.0 * (double)p->dtau / (double)p->beta);
+    A.mass = mass_dev; A.save_interval = save_interval; A.frames = frames_dev; A.ke = ke_dev;
+    A.seed = seed; A.offset = offset; A.flags = flags_dev;
+    return launch(m, A, (cudaStream_t)stream);
+}
+
+int dff_ddpm_sample_host(dff_model_t* m, float* x_host, int batch, int T, const float* const* sched_host, uint64_t seed,
+                         uint32_t* flags_host) {
+    if (!m || !x_host || !sched_host) return fail(DFF_EINVAL, "NULL argument");
+    CUDA_TRY(cudaSetDevice(m->device));
+    const size_t n3 = (size_t)batch * m->N * 3;
+    int rc;
+    if ((rc = ensure_io(m, 0, n3))) return rc;
+    if (m->d_sched_T != (size_t)T) {
+        if (m->d_sched) cudaFree(m->d_sched);
+        m->d_sched = nullptr; m->d_sched_T = 0;
+        CUDA_TRY(cudaMalloc(&m->d_sched, 5 * (size_t)T * sizeof(float)));
+        m->d_sched_T = T;
+    }
+    const float* sp[5];
+    for (int i = 0; i < 5; ++i) {
+        CUDA_TRY(cudaMemcpyAsync(m->d_sched + (size_t)i * T, sched_host[i], T * sizeof(float), cudaMemcpyHostToDevice, 0));
+        sp[i] = m->d_sched + (size_t)i * T;
+    }
+    CUDA_TRY(cudaMemcpyAsync(m->d_io[0], x_host, n3 * sizeof(float), cudaMemcpyHostToDevice, 0));
+    CUDA_TRY(cudaMemsetAsync(m->d_flags, 0, sizeof(uint32_t), 0));
+    if ((rc = dff_ddpm_steps_dev(m, m->d_io[0], batch, T - 1, T, T, sp, nullptr, seed, 0, m->d_flags, nullptr))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(x_host, m->d_io[0], n3 * sizeof(float), cudaMemcpyDeviceToHost, 0));
+    if (flags_host) CUDA_TRY(cudaMemcpyAsync(flags_host, m->d_flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, 0));
+    CUDA_TRY(cudaStreamSynchronize(0));
+    return DFF_OK;
+}
+
+int dff_langevin_run_host(dff_model_t* m, float* x_host, float* v_host, int batch, int n_steps, const dff_md_params_t* p,
+                          const float* mass_host, uint64_t seed, int save_interval, float* frames_host, float* ke_host,
+                          uint32_t* flags_host) {
+    if (!m || !x_host || !p) return fail(DFF_EINVAL, "NULL argument");
+    CUDA_TRY(cudaSetDevice(m->device));
+    const size_t n3 = (size_t)batch * m->N * 3;
+    const size_t nf = save_interval > 0 ? (size_t)(n_steps / save_interval) : 0;
+    int rc;
+    if ((rc = ensure_io(m, 0, n3)) || (rc = ensure_io(m, 1, n3)) || (rc = ensure_io(m, 2, m->N))) return rc;
+    if (frames_host && nf && (rc = ensure_io(m, 3, nf * n3))) return rc;
+    if (ke_host && nf && (rc = ensure_io(m, 4, nf * batch))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(m->d_io[0], x_host, n3 * sizeof(float), cudaMemcpyHostToDevice, 0));
+    if (v_host) CUDA_TRY(cudaMemcpyAsync(m->d_io[1], v_host, n3 * sizeof(float), cudaMemcpyHostToDevice, 0));
+    else CUDA_TRY(cudaMemsetAsync(m->d_io[1], 0, n3 * sizeof(float), 0));
+    if (mass_host) CUDA_TRY(cudaMemcpyAsync(m->d_io[2], mass_host, m->N * sizeof(float), cudaMemcpyHostToDevice, 0));
+    CUDA_TRY(cudaMemsetAsync(m->d_flags, 0, sizeof(uint32_t), 0));
+    rc = dff_langevin_steps_dev(m, m->d_io[0], m->d_io[1], batch, n_steps, p, m->d_io[2], nullptr, seed, 0, save_interval,
+                                (frames_host && nf) ? m->d_io[3] : nullptr, (ke_host && nf) ? m->d_io[4] : nullptr, m->d_flags, nullptr);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(x_host, m->d_io[0], n3 * sizeof(float), cudaMemcpyDeviceToHost, 0));
+    if (v_host) CUDA_TRY(cudaMemcpyAsync(v_host, m->d_io[1], n3 * sizeof(float), cudaMemcpyDeviceToHost, 0));
+    if (frames_host && nf) CUDA_TRY(cudaMemcpyAsync(frames_host, m->d_io[3], nf * n3 * sizeof(float), cudaMemcpyDeviceToHost, 0));
+    if (ke_host && nf) CUDA_TRY(cudaMemcpyAsync(ke_host, m->d_io[4], nf * batch * sizeof(float), cudaMemcpyDeviceToHost, 0));
+    if (flags_host) CUDA_TRY(cudaMemcpyAsync(flags_host, m->d_flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, 0));
+    CUDA_TRY(cudaStreamSynchronize(0));
+    return DFF_OK;
+}
+
+int64_t dff_debug_read_stash(dff_model_t* m, float* out_host, int64_t cap) {
+    if (!m || !out_host) return fail(DFF_EINVAL, "NULL argument");
+    if (cudaSetDevice(m->device) != cudaSuccess) return fail(DFF_ECUDA, "cudaSetDevice failed");
+    const int64_t n = std::min<int64_t>(cap, m->scratch_per_cta);
+    if (cudaDeviceSynchronize() != cudaSuccess) return fail(DFF_ECUDA, "sync failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (cudaMemcpy(out_host, m->d_scratch, n * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess)
+        return fail(DFF_ECUDA, "stash copy failed");
+    return n;
+}
+
+int dff_debug_stash_layout(const dff_model_t* m, int* rows, int* samples, int* npad, int64_t* layer_floats, int64_t offsets[11]) {
+    if (!m) return fail(DFF_EINVAL, "NULL model");
+    const int ri = (m->last_R == 64) ? 1 : 0;
+    if (rows) *rows = m->last_R;
+    if (samples) *samples = m->last_S;
+    if (npad) *npad = m->NP;
+    if (layer_floats) *layer_floats = m->layer_floats[ri];
+    if (offsets) for (int i = 0; i < ST_COUNT; ++i) offsets[i] = m->off[ri][i];
+    return DFF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,142 @@
+// dff_common.cuh -- shared device-side declarations for the fused score/integrator kernel (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dff {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kHeads = 8;          // graph_transformer.py:213
+constexpr int kDimHead = 64;       // graph_transformer.py:213
+constexpr int kInner = kHeads * kDimHead;
+constexpr int kStages = 4;         // weight-slice ring depth
+constexpr int kStageFloats = 3072; // 12 KB per stage: the largest slice ([8][384] / [16][192] floats)
+constexpr int kMaxLayers = 8;
+constexpr int kMaxBeads = 64;
+constexpr float kLnEps = 1e-5f;    // nn.LayerNorm default (graph_transformer.py:182)
+constexpr float kAttnScale = 0.125f; // dim_head ** -0.5 (graph_transformer.py:218)
+
+enum Mode { MODE_SCORE = 0, MODE_DDPM = 1, MODE_BAOAB = 2, MODE_BROWNIAN = 3 };
+
+// One GEMM's weight panel as the kernel consumes it: n_slices contiguous slices of slice_bytes.
+struct Seg {
+    const float* base;
+    uint32_t slice_bytes;
+    uint32_t n_slices;
+};
+
+struct LayerDev {
+    const float* ln1_g; const float* ln1_b;
+    const float* bqkv;      // [8][192]  per head: q bias | k bias | v bias
+    const float* A;         // [8][64][4] folded edge map rows (a0,a1,a2,0): A = W_ekv W_e
+    const float* cvec;      // [512]     c = W_ekv b_e + b_ekv
+    const float* bo;        // [HP]
+    const float* g1a; const float* g1b;   // gate 1: (w_a + w_c), (w_b - w_c)   [H]
+    const float* ln2_g; const float* ln2_b;
+    const float* b1;        // [4H]
+    const float* b2;        // [HP]
+    const float* g2a; const float* g2b;
+};
+
+// Stash regions kept per layer for the reverse pass (offsets in floats inside one layer block).
+enum StashRegion { ST_NIN = 0, ST_STAT1, ST_QKV, ST_P, ST_ATT, ST_G1, ST_M, ST_STAT2, ST_H1, ST_FF, ST_G2, ST_COUNT };
+
+struct ModelDev {
+    int N, NP, H, L, S, nch;        // beads, beads padded to 4, hidden, layers, samples per pass, FF chunks (4H/128)
+    const float* emb;               // [N][H]  W_n[:, i] + b_n
+    const float* embt;              // [H]     W_n[:, N] (time column)
+    const float* dec_w;             // [H]
+    float dec_b;
+    LayerDev layer[kMaxLayers];
+    const Seg* segs;
+    int nseg_fwd, nseg_all;
+    uint32_t nslice_fwd, nslice_all;
+    float* scratch;
+    long long scratch_per_cta;      // floats
+    long long layer_floats;
+    long long off[ST_COUNT];
+};
+
+struct StepArgs {
+    int mode, B, n_steps, need_backward;
+    float* x; float* v; const float* noise;
+    float* eps_out; float* energy_out;
+    // DDPM
+    int t_start, T;
+    const float* sched[5];          // sqrt_recip, sqrt_recipm1, coef1, coef2, logvar
+    // MD
+    float t_norm, force_scale, dt, vscale, noisescale, inv_beta, dtau, bd_sigma;
+    const float* mass;
+    int save_interval;
+    float* frames; float* ke;
+    unsigned long long seed, offset;
+    uint32_t* flags;
+};
+
+// ---------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------- Philox4x32-10 + Box-Muller
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    c[0] = hi1 ^ c[1] ^ k0; c[1] = lo1; c[2] = hi0 ^ c[3] ^ k1; c[3] = lo0;
+}
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        philox_round(c, k0, k1);
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+// Standard normal for (stream element e, step counter): 4 normals per Philox block, element picks its lane.
+__device__ __forceinline__ float philox_normal(unsigned long long seed, unsigned long long counter, uint32_t elem) {
+    uint32_t c[4] = {elem >> 2, (uint32_t)counter, (uint32_t)(counter >> 32), 0x5eedu};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const int pair = (elem >> 1) & 1;
+    const float u1 = ((float)c[2 * pair] + 0.5f) * 2.3283064365386963e-10f;      // (0,1)
+    const float u2 = ((float)c[2 * pair + 1] + 0.5f) * 2.3283064365386963e-10f;
+    const float rad = sqrtf(-2.0f * logf(u1));
+    float sn, cs;
+    sincosf(6.283185307179586f * u2, &sn, &cs);
+    return (elem & 1) ? rad * sn : rad * cs;
+}
+
+}  // namespace dff
