@@ -1,0 +1,161 @@
+"""GPU: the reference-facing Python API (models / dynamics / sample.py mirrors) end to end."""
+import argparse
+import os
+import pickle
+
+import pytest
+import torch
+from torch import nn
+
+from helpers import FORCE_RTOL, GOLDEN, load, net_params, rel_err
+
+pytestmark = pytest.mark.gpu
+SHAPES = {"chignolin": (10, 64, 3), "ala2_fold1": (5, 96, 2), "trp_cage": (20, 128, 3), "protein_g": (56, 128, 3)}
+
+
+def _ddpm(mol, rng="torch"):
+    from models.ddpm import GaussianDiffusion
+    from models.graph_transformer import GraphTransformer
+    N, H, L = SHAPES[mol]
+    std = load(f"score_{mol}.pt")["meta"]["std"]
+    net = GraphTransformer(N, H, "cuda", n_layers=L, use_intrinsic_coords=True, use_abs_coords=False,
+                           use_distances=False, conservative=True)
+    ddpm = GaussianDiffusion(net, torch.eye(N), N, norm_factor=std, loss_weights="higheruntil_100", rng=rng).to("cuda")
+    ddpm.load_state_dict(load(f"weights_{mol}.pt"))
+    return ddpm.eval()
+
+
+@pytest.mark.parametrize("mol", ["chignolin", "protein_g"])
+def test_graph_transformer_forward(mol):
+    ddpm = _ddpm(mol)
+    for c in load(f"score_{mol}.pt")["cases"][:2]:
+        x = c["x"].cuda()
+        tn = torch.full((x.shape[0],), c["t_norm"], device="cuda")
+        f = ddpm.model(x, ddpm.h, tn)
+        e = ddpm.model(x, ddpm.h, tn.reshape(-1, 1, 1), return_energy=True)
+        assert f.shape == x.shape and e.shape == (x.shape[0], x.shape[1], 1)
+        assert rel_err(f, c["forces"]) < FORCE_RTOL and rel_err(e[..., 0], c["energy"]) < FORCE_RTOL
+
+
+def test_engine_repacks_after_load_state_dict():
+    ddpm = _ddpm("chignolin")
+    c = load("score_chignolin.pt")["cases"][0]
+    x = c["x"].cuda()
+    f0 = ddpm.model(x, ddpm.h, torch.tensor([c["t_norm"]], device="cuda"))
+    with torch.no_grad():
+        ddpm.model.node_decoder.weight.mul_(2.0)
+    f1 = ddpm.model(x, ddpm.h, torch.tensor([c["t_norm"]], device="cuda"))
+    assert rel_err(f1, 2 * f0) < 1e-5
+
+
+def test_p_sample_matches_reference_chain():
+    """Per-step API (p_sample with torch ops around the CUDA score) on the reference's chain, with its RNG stream emulated."""
+    ddpm = _ddpm("chignolin")
+    ch = load("ddpm_chignolin.pt")["chains"][0]
+    x = ch["x_init"].cuda()
+    for s in range(ch["steps"]):
+        t = torch.full((x.shape[0],), ch["t_start"] - s, device="cuda", dtype=torch.long)
+        mean, _, logvar = ddpm.p_mean_variance(x, t)
+        z = ch["noise"][s].cuda()
+        x = mean + (0.5 * logvar).exp() * (z - z.mean(1, keepdim=True))
+        x = x - x.mean(1, keepdim=True)
+        assert rel_err(x, ch["x_steps"][s]) < 2e-4
+
+
+def test_sample_rng_stream_is_torch_and_reproducible():
+    ddpm = _ddpm("ala2_fold1")
+    torch.manual_seed(11)
+    a = ddpm.sample(batch_size=8)
+    torch.manual_seed(11)
+    b = ddpm.sample(batch_size=8)
+    assert torch.equal(a, b) and a.shape == (8, 5, 3) and torch.isfinite(a).all()
+    # the noise buffer is filled by the same generator calls the reference makes (randn_like per step)
+    torch.manual_seed(3)
+    r0 = torch.randn(8, 5, 3, device="cuda"); r1 = torch.randn_like(r0)
+    torch.manual_seed(3)
+    q0 = torch.randn(8, 5, 3, device="cuda"); buf = torch.empty(2, 8, 5, 3, device="cuda"); torch.randn((8, 5, 3), device="cuda", out=buf[0])
+    assert torch.equal(r0, q0) and torch.equal(r1, buf[0])
+    assert float(a.mean(1).abs().max()) < 1e-3 * load("score_ala2_fold1.pt")["meta"]["std"] + 1e-4
+
+
+@pytest.mark.parametrize("mol", ["chignolin", "ala2_fold1"])
+def test_langevin_diffusion_reproduces_reference_runs(mol):
+    """LangevinDiffusion(...).sample() with rng='torch' and the same torch seed == the reference's trajectory."""
+    from dynamics.langevin import LangevinDiffusion
+    ddpm = _ddpm(mol)
+    g = load(f"langevin_{mol}.pt")
+    for r, seed in zip(g["runs"], (21, 22, 23)):
+        torch.manual_seed(seed)
+        sim = LangevinDiffusion(ddpm, r["init_mol"].clone(), r["steps"], save_interval=r["save_interval"], t=r["t"],
+                                diffusion_steps=1000, temp_data=r["temp"], temp_sim=r["temp"], dt=None, masses=r["masses"],
+                                friction=r["friction"], kb="consistent", rng="torch")
+        traj = sim.sample()
+        assert traj.shape == r["traj"].shape
+        assert rel_err(traj, r["traj"]) < 2e-4, (mol, r["friction"], rel_err(traj, r["traj"]))
+        if r["kinetic"] is not None:
+            assert rel_err(torch.as_tensor(sim.sim.kinetic_energies), r["kinetic"]) < 5e-4
+
+
+def _model_dir(tmp_path, mol, mol_name):
+    """A --model_path directory in the reference's format built from the golden weights."""
+    from oracle.weights import ema_checkpoint
+    N, H, L = SHAPES[mol]
+    ema = load(f"weights_{mol}.pt")
+    ck = {"step": 1, "ema": {"initted": torch.tensor([1.0]), "step": torch.tensor([1])}}
+    for top in ("online_model.", "ema_model."):
+        for k, v in ema.items():
+            ck["ema"][top + k] = v
+    d = tmp_path / mol
+    d.mkdir()
+    torch.save(ck, d / "model-best.pt")
+    args = argparse.Namespace(mol=mol_name, fold=1, mean0=True, shuffle_data_before_splitting=True, scale_data=True,
+                              hidden_features_gnn=H, num_layers_gnn=L, use_intrinsic_coords=True, use_abs_coords=False,
+                              use_distances=False, conservative=True, diffusion_steps=1000, loss_weights="higheruntil_100",
+                              backbone_network="graph-transformer", activation=nn.Tanh())
+    pickle.dump(args, open(d / "args.pickle", "wb"))
+    return str(d)
+
+
+def test_sample_cli_iid_and_langevin(tmp_path):
+    import sample
+    from dff_b200.pdb import load_pdb
+    mp = _model_dir(tmp_path, "chignolin", "CHIGNOLIN")
+    a = sample.build_parser().parse_args(["--model_path", mp, "--gen_mode", "iid", "--num_samples_eval", "40", "--batch_size_gen", "16", "--seed", "1"])
+    out = sample.main(a)
+    saved = torch.load(os.path.join(mp, "main_eval_output_iid", "sample-iid.pt"))
+    assert saved.shape == (40, 10, 3) and saved.dtype == torch.float32 and torch.equal(saved, out) and torch.isfinite(saved).all()
+    top, xyz = load_pdb(os.path.join(mp, "main_eval_output_iid", "sample-iid.pdb"))
+    assert top.n_atoms == 10
+    # C-alpha neighbours sit ~3.8 A apart in any sensible sample
+    d = (saved[:, 1:] - saved[:, :-1]).norm(dim=-1)
+    assert 3.3 < float(d.median()) < 4.3
+    a = sample.build_parser().parse_args(["--model_path", mp, "--gen_mode", "langevin", "--parallel_sim", "12", "--batch_size_gen", "12",
+                                          "--n_timesteps", "60", "--save_interval", "20", "--seed", "2", "--append_exp_name", "t"])
+    out = sample.main(a)
+    saved = torch.load(os.path.join(mp, "main_eval_output_langevin_t", "sample-langevin.pt"))
+    assert saved.shape == (12 * 3, 10, 3) and torch.isfinite(saved).all()
+    d = (saved[:, 1:] - saved[:, :-1]).norm(dim=-1)
+    assert 3.3 < float(d.median()) < 4.3
+
+
+def test_distribution_matches_reference_samples():
+    """Distributional parity (north_star): pairwise-distance statistics of GPU samples vs samples drawn by the
+    unmodified reference on CPU (tests/golden/dist_reference.pt), for both RNG modes."""
+    path = os.path.join(GOLDEN, "dist_reference.pt")
+    if not os.path.exists(path):
+        pytest.skip("distribution fixture not generated")
+    from oracle import sampler_ref
+    ref = torch.load(path)
+    for mol in ref:
+        for rng in ("torch", "philox"):
+            ddpm = _ddpm(mol, rng=rng)
+            torch.manual_seed(5)
+            xs = ddpm.sample(batch_size=4096).cpu()
+            d = sampler_ref.pwd_triu(xs)
+            r = ref[mol]["iid"]
+            se = (r["std"] ** 2 / r["n"] + d.std(0) ** 2 / d.shape[0]).sqrt()
+            zscore = ((d.mean(0) - r["mean"]).abs() / se).max()
+            assert float(zscore) < 5.0, (mol, rng, float(zscore))
+            assert float(((d.std(0) / r["std"]) - 1).abs().max()) < 0.25, (mol, rng)
+            h = torch.histc(d.flatten(), bins=60, min=0.0, max=r["hi"])
+            assert sampler_ref.js_divergence(h.numpy(), r["hist"].numpy()) < 5e-3, (mol, rng)

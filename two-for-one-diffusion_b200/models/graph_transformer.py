@@ -1,0 +1,119 @@
+"""`GraphTransformer` with the reference's constructor, state-dict layout and forward() contract
+(models/graph_transformer.py:18-114), executed by the fused sm_100a kernel in libdff_b200.so.
+
+The nn.Module tree below exists ONLY to own parameters under the reference's checkpoint key names
+(`graphtransformer.layers.{l}.0.0.fn.to_q.weight`, ... SURVEY.md 3.4) so `load_state_dict` of a shipped
+`model-best.pt["ema"]` works unchanged.  None of these sub-modules has a forward(): the arithmetic
+(edge build, edge-conditioned attention, gated residual MLP, -dE/dx) lives in CUDA, and there is no CPU path.
+"""
+from typing import Optional
+
+import torch
+from torch import nn
+
+from dff_b200 import DffError, ScoreEngine
+
+HEADS, DIM_HEAD = 8, 64      # reference graph_transformer.py:213 (never overridden)
+
+
+class _Params(nn.Module):
+    """Parameter holder; calling it is an error by design."""
+
+    def forward(self, *a, **k):
+        raise DffError("this sub-module only stores parameters; call GraphTransformer.forward (CUDA)")
+
+
+class Attention(_Params):
+    def __init__(self, dim, edge_dim):
+        super().__init__()
+        inner = HEADS * DIM_HEAD
+        self.to_q = nn.Linear(dim, inner)
+        self.to_kv = nn.Linear(dim, 2 * inner)
+        self.edges_to_kv = nn.Linear(edge_dim, inner)
+        self.to_out = nn.Linear(inner, dim)
+
+
+class PreNorm(_Params):
+    def __init__(self, dim, fn):
+        super().__init__()
+        self.fn = fn
+        self.norm = nn.LayerNorm(dim)
+
+
+class GatedResidual(_Params):
+    def __init__(self, dim):
+        super().__init__()
+        self.proj = nn.Sequential(nn.Linear(3 * dim, 1, bias=False), nn.Sigmoid())
+
+
+def _feed_forward(dim, mult=4):
+    return nn.Sequential(nn.Linear(dim, dim * mult), nn.GELU(), nn.Linear(dim * mult, dim))
+
+
+class GraphTransformerLucid(_Params):
+    def __init__(self, dim, depth, edge_dim):
+        super().__init__()
+        self.layers = nn.ModuleList(
+            nn.ModuleList([nn.ModuleList([PreNorm(dim, Attention(dim, edge_dim)), GatedResidual(dim)]),
+                           nn.ModuleList([PreNorm(dim, _feed_forward(dim)), GatedResidual(dim)])])
+            for _ in range(depth))
+
+
+class GraphTransformer(nn.Module):
+    def __init__(self, num_beads, hidden_nf, device="cpu", n_layers=4, use_intrinsic_coords: bool = False,
+                 use_abs_coords: bool = True, use_distances: bool = True, conservative: bool = True):
+        super().__init__()
+        self.device = device
+        self.num_beads, self.hidden_nf, self.n_layers = num_beads, hidden_nf, n_layers
+        self.use_intrinsic_coords, self.use_distances = use_intrinsic_coords, use_distances
+        self.use_abs_coords, self.conservative = use_abs_coords, conservative
+        if not (use_intrinsic_coords and not use_abs_coords and not use_distances and conservative):
+            raise DffError("the B200 kernel implements the configuration of every shipped checkpoint: "
+                           "use_intrinsic_coords=True, use_abs_coords=False, use_distances=False, conservative=True "
+                           "(other edge modes are listed as 'next' in SURVEY.md 8f)")
+        self.node_embedding = nn.Linear(num_beads + 1, hidden_nf)
+        self.edge_embedding = nn.Linear(3, hidden_nf)
+        self.node_decoder = nn.Linear(hidden_nf, 1)
+        self.graphtransformer = GraphTransformerLucid(hidden_nf, n_layers, hidden_nf)
+        self.max_batch = 4096
+        self._eng, self._eng_key = None, None
+        self.to(self.device)
+
+    # ---- engine management: re-pack whenever parameters change (load_state_dict, .to(), optimizer step ...)
+    def _param_key(self):
+        ps = list(self.parameters())
+        return (str(ps[0].device), tuple(p._version for p in ps), tuple(p.data_ptr() for p in ps), self.max_batch)
+
+    def engine(self, min_batch: int = 1) -> ScoreEngine:
+        if min_batch > self.max_batch:
+            self.max_batch = int(min_batch)
+        key = self._param_key()
+        if self._eng is None or key != self._eng_key:
+            dev = next(self.parameters()).device
+            if dev.type != "cuda":
+                raise DffError(f"GraphTransformer parameters are on {dev}; the score network only runs on a CUDA "
+                               "device (B200, sm_100a) -- there is no CPU fallback")
+            if self._eng is not None:
+                self._eng.close()
+            state = {k: v.detach() for k, v in self.state_dict().items()}
+            self._eng = ScoreEngine(state, device=dev, max_batch=self.max_batch)
+            self._eng_key = key
+        return self._eng
+
+    @staticmethod
+    def _shared_t(t) -> float:
+        if torch.is_tensor(t):
+            flat = t.reshape(-1)
+            return float(flat[0])
+        return float(t)
+
+    def forward(self, x, h, t, return_energy=False, alphas: Optional[torch.Tensor] = None):
+        """x [B,N,3]; h [N,N] bead one-hot (identity); t [B] / [B,1,1] = step/T shared by the batch.
+        Returns forces (= -dE/dx, the epsilon prediction) [B,N,3], or energies [B,N,1] if return_energy.
+        `alphas` is accepted and unused, exactly like the reference (graph_transformer.py:83)."""
+        if h is not None and tuple(h.shape) != (self.num_beads, self.num_beads):
+            raise DffError(f"h must be the [{self.num_beads},{self.num_beads}] bead one-hot matrix")
+        eng = self.engine(x.shape[0])
+        xin = x.detach().to(eng.device, torch.float32).contiguous()
+        eps, en = eng.score(xin, self._shared_t(t), want_forces=not return_energy, want_energy=return_energy)
+        return en.unsqueeze(-1) if return_energy else eps
