@@ -49,11 +49,9 @@ struct dff_model {
     int N = 0, NP = 0, H = 0, HP = 0, L = 0, nch = 0;
     int max_batch = 0;
     float* d_weights = nullptr;     // every packed tensor + GEMM panel
-    Seg* d_segs = nullptr;
+    Seg* d_segs[2] = {nullptr, nullptr};
     float* d_scratch = nullptr;
-    ModelDev md{};                  // template; S / stash geometry are filled per launch
-    int nseg_fwd = 0, nseg_all = 0;
-    uint32_t nslice_fwd = 0, nslice_all = 0;
+    ModelDev md[2];                 // [0]: R=32, 2 heads per chunk; [1]: R=64, 1 head per chunk.  S is filled per launch
     long long layer_floats[2] = {0, 0};          // for R = 32, 64
     long long off[2][ST_COUNT];
     long long scratch_per_cta = 0;               // floats (sized for R = 64)
@@ -94,11 +92,11 @@ struct Packer {
     }
 };
 
-template <int HP, int R>
+template <int HP, int R, int HC>
 int launch_cfg(dff_model* m, const ModelDev& M, const StepArgs& A, int grid, cudaStream_t stream) {
     static bool attr_set[8] = {false};
-    auto kern = dff_fused_kernel<HP, R>;
-    const size_t smem = Cfg<HP, R>::kSmemBytes;
+    auto kern = dff_fused_kernel<HP, R, HC>;
+    const size_t smem = Cfg<HP, R, HC>::kSmemBytes;
     if (!attr_set[m->device & 7]) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set[m->device & 7] = true;
@@ -120,15 +118,13 @@ int launch(dff_model* m, StepArgs& A, cudaStream_t stream) {
     if (s32 >= 1 && need <= s32) { R = 32; S = std::max(need, 1); }
     else { R = 64; S = std::min(s64, std::max(need, 1)); }
     const int ri = (R == 64) ? 1 : 0;
-    ModelDev M = m->md;
+    ModelDev M = m->md[ri];
     M.S = S;
-    M.layer_floats = m->layer_floats[ri];
-    for (int i = 0; i < ST_COUNT; ++i) M.off[i] = m->off[ri][i];
     const int n_groups = (A.B + S - 1) / S;
     const int grid = std::min(n_groups, m->num_sms);
     m->last_R = R; m->last_S = S;
-    if (m->HP == 64) return (R == 64) ? launch_cfg<64, 64>(m, M, A, grid, stream) : launch_cfg<64, 32>(m, M, A, grid, stream);
-    return (R == 64) ? launch_cfg<128, 64>(m, M, A, grid, stream) : launch_cfg<128, 32>(m, M, A, grid, stream);
+    if (m->HP == 64) return (R == 64) ? launch_cfg<64, 64, 1>(m, M, A, grid, stream) : launch_cfg<64, 32, 2>(m, M, A, grid, stream);
+    return (R == 64) ? launch_cfg<128, 64, 1>(m, M, A, grid, stream) : launch_cfg<128, 32, 2>(m, M, A, grid, stream);
 }
 
 int ensure_io(dff_model* m, int slot, size_t floats) {
@@ -185,7 +181,7 @@ int dff_model_create(dff_model_t** out, int device, int num_beads, int hidden, i
     const float* Wd = w[4]; const float* bd = w[5];
 
     Packer P;
-    struct LayerOff { size_t ln1_g, ln1_b, bqkv, A, cvec, bo, g1a, g1b, ln2_g, ln2_b, b1, b2, g2a, g2b; };
+    struct LayerOff { size_t ln1_g, ln1_b, bqkv[2], A, cvec, bo, g1a, g1b, ln2_g, ln2_b, b1, b2, g2a, g2b; };
     std::vector<LayerOff> lo(L);
     const size_t o_emb = P.alloc((size_t)N * H), o_embt = P.alloc(H), o_dec = P.alloc(H);
     for (int i = 0; i < N; ++i)
@@ -193,12 +189,14 @@ int dff_model_create(dff_model_t** out, int device, int num_beads, int hidden, i
     for (int d = 0; d < H; ++d) { P.buf[o_embt + d] = Wn[(size_t)d * (N + 1) + N]; P.buf[o_dec + d] = Wd[d]; }
 
     auto LW = [&](int l, int k) { return w[DFF_NUM_GLOBAL_WEIGHTS + DFF_NUM_LAYER_WEIGHTS * l + k]; };
+    const int HCs[2] = {2, 1};      // heads per chunk of configuration 0 (R=32) and 1 (R=64)
     for (int l = 0; l < L; ++l) {
         LayerOff& o = lo[l];
         const float *ln1g = LW(l, 0), *ln1b = LW(l, 1), *bq = LW(l, 3), *bkv = LW(l, 5), *Wekv = LW(l, 6), *bekv = LW(l, 7),
                     *bo = LW(l, 9), *g1 = LW(l, 10), *ln2g = LW(l, 11), *ln2b = LW(l, 12), *b1 = LW(l, 14), *b2 = LW(l, 16),
                     *g2 = LW(l, 17);
-        o.ln1_g = P.alloc(H); o.ln1_b = P.alloc(H); o.bqkv = P.alloc(8 * 192); o.A = P.alloc(512 * 4); o.cvec = P.alloc(512);
+        o.ln1_g = P.alloc(H); o.ln1_b = P.alloc(H); o.bqkv[0] = P.alloc(8 * 192); o.bqkv[1] = P.alloc(8 * 192);
+        o.A = P.alloc(512 * 4); o.cvec = P.alloc(512);
         o.bo = P.alloc(HP); o.g1a = P.alloc(H); o.g1b = P.alloc(H); o.ln2_g = P.alloc(H); o.ln2_b = P.alloc(H);
         o.b1 = P.alloc(4 * H); o.b2 = P.alloc(HP); o.g2a = P.alloc(H); o.g2b = P.alloc(H);
         for (int d = 0; d < H; ++d) {
@@ -209,12 +207,15 @@ int dff_model_create(dff_model_t** out, int device, int num_beads, int hidden, i
             P.buf[o.g2a + d] = g2[d] + g2[2 * H + d]; P.buf[o.g2b + d] = g2[H + d] - g2[2 * H + d];
         }
         for (int j = 0; j < 4 * H; ++j) P.buf[o.b1 + j] = b1[j];
-        for (int h = 0; h < 8; ++h)
-            for (int j = 0; j < 64; ++j) {
-                P.buf[o.bqkv + h * 192 + j] = bq[h * 64 + j];
-                P.buf[o.bqkv + h * 192 + 64 + j] = bkv[h * 64 + j];
-                P.buf[o.bqkv + h * 192 + 128 + j] = bkv[512 + h * 64 + j];
-            }
+        for (int ci = 0; ci < 2; ++ci) {           // bias of chunk c: [q of its heads | k | v]
+            const int CWQ = 64 * HCs[ci];
+            for (int c2 = 0; c2 < 512 / CWQ; ++c2)
+                for (int j = 0; j < CWQ; ++j) {
+                    P.buf[o.bqkv[ci] + c2 * 3 * CWQ + j] = bq[c2 * CWQ + j];
+                    P.buf[o.bqkv[ci] + c2 * 3 * CWQ + CWQ + j] = bkv[c2 * CWQ + j];
+                    P.buf[o.bqkv[ci] + c2 * 3 * CWQ + 2 * CWQ + j] = bkv[512 + c2 * CWQ + j];
+                }
+        }
         // fold edge_embedding into edges_to_kv (exact: no nonlinearity between them, graph_transformer.py:96,235,288)
         for (int j = 0; j < 512; ++j) {
             double a[3] = {0, 0, 0}, cc = bekv[j];
@@ -228,86 +229,96 @@ int dff_model_create(dff_model_t** out, int device, int num_beads, int hidden, i
         }
     }
 
-    // GEMM panels [K][NC] in the exact order the kernel consumes them
-    std::vector<SegHost> segs;
-    auto panel = [&](int K, int NC, auto&& fill /* (k, c) -> value */) {
-        const size_t o = P.alloc((size_t)K * NC);
-        for (int k = 0; k < K; ++k)
-            for (int c2 = 0; c2 < NC; ++c2) P.buf[o + (size_t)k * NC + c2] = fill(k, c2);
-        const int KS = ks_for(NC);
-        segs.push_back({o, (uint32_t)(KS * NC * sizeof(float)), (uint32_t)(K / KS)});
-    };
-    for (int l = 0; l < L; ++l) {
-        const float *Wq = LW(l, 2), *Wkv = LW(l, 4), *Wo = LW(l, 8), *W1 = LW(l, 13), *W2 = LW(l, 15);
-        for (int h = 0; h < 8; ++h) {
-            panel(H, 192, [&](int k, int c2) {
-                const int t = c2 / 64, j = c2 % 64;
-                return t == 0 ? Wq[(size_t)(h * 64 + j) * H + k]
-                              : Wkv[(size_t)((t == 1 ? 0 : 512) + h * 64 + j) * H + k];
-            });
-            panel(64, HP, [&](int k, int d) { return d < H ? Wo[(size_t)d * 512 + h * 64 + k] : 0.f; });
-        }
-        for (int ch = 0; ch < nch; ++ch) {
-            panel(H, 128, [&](int k, int j) { return W1[(size_t)(ch * 128 + j) * H + k]; });
-            panel(128, HP, [&](int k, int d) { return d < H ? W2[(size_t)d * 4 * H + ch * 128 + k] : 0.f; });
-        }
-    }
-    m->nseg_fwd = (int)segs.size();
-    for (int l = L - 1; l >= 0; --l) {
-        const float *Wq = LW(l, 2), *Wkv = LW(l, 4), *Wo = LW(l, 8), *W1 = LW(l, 13), *W2 = LW(l, 15);
-        for (int ch = 0; ch < nch; ++ch) {
-            panel(H, 128, [&](int d, int j) { return W2[(size_t)d * 4 * H + ch * 128 + j]; });
-            panel(128, HP, [&](int j, int d) { return d < H ? W1[(size_t)(ch * 128 + j) * H + d] : 0.f; });
-        }
-        for (int h = 0; h < 8; ++h) {
-            panel(H, 64, [&](int d, int j) { return Wo[(size_t)d * 512 + h * 64 + j]; });
-            if (l > 0)
-                panel(192, HP, [&](int k, int d) {   // rows: dv' | dk' | dq
-                    if (d >= H) return 0.f;
-                    const int t = k / 64, j = k % 64;
-                    return t == 0 ? Wkv[(size_t)(512 + h * 64 + j) * H + d]
-                         : t == 1 ? Wkv[(size_t)(h * 64 + j) * H + d]
-                                  : Wq[(size_t)(h * 64 + j) * H + d];
+    // GEMM panels [K][NC] in the exact order the kernel consumes them, once per configuration
+    std::vector<SegHost> segs[2];
+    int nseg_fwd[2] = {0, 0};
+    uint32_t nslice_fwd[2] = {0, 0}, nslice_all[2] = {0, 0};
+    for (int ci = 0; ci < 2; ++ci) {
+        const int CWQ = 64 * HCs[ci], NCHK = 512 / CWQ;
+        auto panel = [&](int K, int NC, auto&& fill /* (k, c) -> value */) {
+            const int NCP = NC + kWPad;          // padded row stride: conflict-free MMA B-fragment loads
+            const size_t o = P.alloc((size_t)K * NCP);
+            for (int k = 0; k < K; ++k)
+                for (int c2 = 0; c2 < NC; ++c2) P.buf[o + (size_t)k * NCP + c2] = fill(k, c2);
+            const int KS = ks_for(NC);
+            segs[ci].push_back({o, (uint32_t)(KS * NCP * sizeof(float)), (uint32_t)(K / KS)});
+        };
+        for (int l = 0; l < L; ++l) {
+            const float *Wq = LW(l, 2), *Wkv = LW(l, 4), *Wo = LW(l, 8), *W1 = LW(l, 13), *W2 = LW(l, 15);
+            for (int hc = 0; hc < NCHK; ++hc) {
+                panel(H, 3 * CWQ, [&](int k, int c2) {
+                    const int t = c2 / CWQ, j = c2 % CWQ;
+                    return t == 0 ? Wq[(size_t)(hc * CWQ + j) * H + k]
+                                  : Wkv[(size_t)((t == 1 ? 0 : 512) + hc * CWQ + j) * H + k];
                 });
+                panel(CWQ, HP, [&](int k, int d) { return d < H ? Wo[(size_t)d * 512 + hc * CWQ + k] : 0.f; });
+            }
+            for (int ch = 0; ch < nch; ++ch) {
+                panel(H, 128, [&](int k, int j) { return W1[(size_t)(ch * 128 + j) * H + k]; });
+                panel(128, HP, [&](int k, int d) { return d < H ? W2[(size_t)d * 4 * H + ch * 128 + k] : 0.f; });
+            }
         }
-    }
-    m->nseg_all = (int)segs.size();
-    for (int i = 0; i < m->nseg_all; ++i) {
-        if (i < m->nseg_fwd) m->nslice_fwd += segs[i].n_slices;
-        m->nslice_all += segs[i].n_slices;
+        nseg_fwd[ci] = (int)segs[ci].size();
+        for (int l = L - 1; l >= 0; --l) {
+            const float *Wq = LW(l, 2), *Wkv = LW(l, 4), *Wo = LW(l, 8), *W1 = LW(l, 13), *W2 = LW(l, 15);
+            for (int ch = 0; ch < nch; ++ch) {
+                panel(H, 128, [&](int d, int j) { return W2[(size_t)d * 4 * H + ch * 128 + j]; });
+                panel(128, HP, [&](int j, int d) { return d < H ? W1[(size_t)(ch * 128 + j) * H + d] : 0.f; });
+            }
+            for (int hc = 0; hc < NCHK; ++hc) {
+                panel(H, CWQ, [&](int d, int j) { return Wo[(size_t)d * 512 + hc * CWQ + j]; });
+                if (l > 0)
+                    panel(3 * CWQ, HP, [&](int k, int d) {   // rows: dv' | dk' | dq of the chunk's heads
+                        if (d >= H) return 0.f;
+                        const int t = k / CWQ, j = k % CWQ;
+                        return t == 0 ? Wkv[(size_t)(512 + hc * CWQ + j) * H + d]
+                             : t == 1 ? Wkv[(size_t)(hc * CWQ + j) * H + d]
+                                      : Wq[(size_t)(hc * CWQ + j) * H + d];
+                    });
+            }
+        }
+        for (int i = 0; i < (int)segs[ci].size(); ++i) {
+            if (i < nseg_fwd[ci]) nslice_fwd[ci] += segs[ci][i].n_slices;
+            nslice_all[ci] += segs[ci][i].n_slices;
+        }
     }
 
     auto cleanup = [&]() { dff_model_destroy(m); };
     if (cudaMalloc(&m->d_weights, P.buf.size() * sizeof(float)) != cudaSuccess) { cleanup(); return fail(DFF_ENOMEM, "cudaMalloc weights failed"); }
     if (cudaMemcpy(m->d_weights, P.buf.data(), P.buf.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) { cleanup(); return fail(DFF_ECUDA, "weight upload failed"); }
-    std::vector<Seg> hs(segs.size());
-    for (size_t i = 0; i < segs.size(); ++i) hs[i] = Seg{m->d_weights + segs[i].offset, segs[i].slice_bytes, segs[i].n_slices};
-    if (cudaMalloc(&m->d_segs, hs.size() * sizeof(Seg)) != cudaSuccess) { cleanup(); return fail(DFF_ENOMEM, "cudaMalloc segs failed"); }
-    if (cudaMemcpy(m->d_segs, hs.data(), hs.size() * sizeof(Seg), cudaMemcpyHostToDevice) != cudaSuccess) { cleanup(); return fail(DFF_ECUDA, "segment upload failed"); }
+    for (int ci = 0; ci < 2; ++ci) {
+        std::vector<Seg> hs(segs[ci].size());
+        for (size_t i = 0; i < hs.size(); ++i) hs[i] = Seg{m->d_weights + segs[ci][i].offset, segs[ci][i].slice_bytes, segs[ci][i].n_slices};
+        if (cudaMalloc(&m->d_segs[ci], hs.size() * sizeof(Seg)) != cudaSuccess) { cleanup(); return fail(DFF_ENOMEM, "cudaMalloc segs failed"); }
+        if (cudaMemcpy(m->d_segs[ci], hs.data(), hs.size() * sizeof(Seg), cudaMemcpyHostToDevice) != cudaSuccess) { cleanup(); return fail(DFF_ECUDA, "segment upload failed"); }
+    }
 
     stash_geometry(32, m->NP, H, m->off[0], &m->layer_floats[0]);
     stash_geometry(64, m->NP, H, m->off[1], &m->layer_floats[1]);
     m->scratch_per_cta = (long long)L * m->layer_floats[1] + 64LL * H;
-    const int s_max = std::max(1, 64 / N);
     const int n_ctas = std::min(m->num_sms, std::max(1, max_batch));
-    (void)s_max;
     if (cudaMalloc(&m->d_scratch, (size_t)n_ctas * m->scratch_per_cta * sizeof(float)) != cudaSuccess) { cleanup(); return fail(DFF_ENOMEM, "cudaMalloc scratch failed"); }
     if (cudaMalloc(&m->d_flags, sizeof(uint32_t)) != cudaSuccess) { cleanup(); return fail(DFF_ENOMEM, "cudaMalloc flags failed"); }
 
-    ModelDev& M = m->md;
-    M.N = N; M.NP = m->NP; M.H = H; M.L = L; M.S = 1; M.nch = nch;
-    M.emb = m->d_weights + o_emb; M.embt = m->d_weights + o_embt; M.dec_w = m->d_weights + o_dec; M.dec_b = bd[0];
-    for (int l = 0; l < L; ++l) {
-        const LayerOff& o = lo[l];
-        LayerDev& D = M.layer[l];
-        const float* b = m->d_weights;
-        D.ln1_g = b + o.ln1_g; D.ln1_b = b + o.ln1_b; D.bqkv = b + o.bqkv; D.A = b + o.A; D.cvec = b + o.cvec; D.bo = b + o.bo;
-        D.g1a = b + o.g1a; D.g1b = b + o.g1b; D.ln2_g = b + o.ln2_g; D.ln2_b = b + o.ln2_b; D.b1 = b + o.b1; D.b2 = b + o.b2;
-        D.g2a = b + o.g2a; D.g2b = b + o.g2b;
+    for (int ci = 0; ci < 2; ++ci) {
+        ModelDev& M = m->md[ci];
+        M = ModelDev{};
+        M.N = N; M.NP = m->NP; M.H = H; M.L = L; M.S = 1; M.nch = nch;
+        M.emb = m->d_weights + o_emb; M.embt = m->d_weights + o_embt; M.dec_w = m->d_weights + o_dec; M.dec_b = bd[0];
+        for (int l = 0; l < L; ++l) {
+            const LayerOff& o = lo[l];
+            LayerDev& D = M.layer[l];
+            const float* b = m->d_weights;
+            D.ln1_g = b + o.ln1_g; D.ln1_b = b + o.ln1_b; D.bqkv = b + o.bqkv[ci]; D.A = b + o.A; D.cvec = b + o.cvec; D.bo = b + o.bo;
+            D.g1a = b + o.g1a; D.g1b = b + o.g1b; D.ln2_g = b + o.ln2_g; D.ln2_b = b + o.ln2_b; D.b1 = b + o.b1; D.b2 = b + o.b2;
+            D.g2a = b + o.g2a; D.g2b = b + o.g2b;
+        }
+        M.segs = m->d_segs[ci]; M.nseg_fwd = nseg_fwd[ci]; M.nseg_all = (int)segs[ci].size();
+        M.nslice_fwd = nslice_fwd[ci]; M.nslice_all = nslice_all[ci];
+        M.scratch = m->d_scratch; M.scratch_per_cta = m->scratch_per_cta;
+        M.layer_floats = m->layer_floats[ci];
+        for (int i = 0; i < ST_COUNT; ++i) M.off[i] = m->off[ci][i];
     }
-    M.segs = m->d_segs; M.nseg_fwd = m->nseg_fwd; M.nseg_all = m->nseg_all;
-    M.nslice_fwd = m->nslice_fwd; M.nslice_all = m->nslice_all;
-    M.scratch = m->d_scratch; M.scratch_per_cta = m->scratch_per_cta;
     *out = m;
     return DFF_OK;
 }
@@ -316,7 +327,7 @@ void dff_model_destroy(dff_model_t* m) {
     if (!m) return;
     cudaSetDevice(m->device);
     if (m->d_weights) cudaFree(m->d_weights);
-    if (m->d_segs) cudaFree(m->d_segs);
+    for (auto p : m->d_segs) if (p) cudaFree(p);
     if (m->d_scratch) cudaFree(m->d_scratch);
     if (m->d_flags) cudaFree(m->d_flags);
     if (m->d_sched) cudaFree(m->d_sched);

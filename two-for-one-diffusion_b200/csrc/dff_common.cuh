@@ -5,15 +5,19 @@
 
 namespace dff {
 
-constexpr int kThreads = 256;
+#ifndef DFF_THREADS
+#define DFF_THREADS 256
+#endif
+constexpr int kThreads = DFF_THREADS;
 constexpr int kWarps = kThreads / 32;
 constexpr int kHeads = 8;          // graph_transformer.py:213
 constexpr int kDimHead = 64;       // graph_transformer.py:213
 constexpr int kInner = kHeads * kDimHead;
 constexpr int kStages = 4;         // weight-slice ring depth
-constexpr int kStageFloats = 3072; // 12 KB per stage: the largest slice ([8][384] / [16][192] floats)
+constexpr int kStageFloats = 3200; // 12.5 KB per stage: the largest slice, [16][192 + 8] floats
 constexpr int kMaxLayers = 8;
 constexpr int kMaxBeads = 64;
+constexpr int kSegCap = 200;       // segment-table entries cached in shared memory
 constexpr float kLnEps = 1e-5f;    // nn.LayerNorm default (graph_transformer.py:182)
 constexpr float kAttnScale = 0.125f; // dim_head ** -0.5 (graph_transformer.py:218)
 
@@ -84,6 +88,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t"
@@ -105,6 +112,14 @@ __device__ __forceinline__ void fence_barrier_init() {
 }
 __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// 16-byte Ampere-style async copy global -> shared (SASS: LDGSTS), used for the stash reloads
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

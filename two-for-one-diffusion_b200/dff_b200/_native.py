@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdff_b200.so")
+LIB_PATH = os.environ.get("DFF_LIB_PATH") or os.path.join(_HERE, "libdff_b200.so")
 
 DFF_MD_BAOAB = 0
 DFF_MD_BROWNIAN = 1
