@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -55,6 +56,7 @@ struct dff_model {
     long long layer_floats[2] = {0, 0};          // for R = 32, 64
     long long off[2][ST_COUNT];
     long long scratch_per_cta = 0;               // floats (sized for R = 64)
+    int scratch_ctas = 0;
     int64_t launches = 0;
     // staging for the *_host entry points
     float* d_io[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -92,11 +94,11 @@ struct Packer {
     }
 };
 
-template <int HP, int R, int HC>
+template <class C, int MINB>
 int launch_cfg(dff_model* m, const ModelDev& M, const StepArgs& A, int grid, cudaStream_t stream) {
     static bool attr_set[8] = {false};
-    auto kern = dff_fused_kernel<HP, R, HC>;
-    const size_t smem = Cfg<HP, R, HC>::kSmemBytes;
+    auto kern = dff_fused_kernel<C, MINB>;
+    const size_t smem = C::kSmemBytes;
     if (!attr_set[m->device & 7]) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set[m->device & 7] = true;
@@ -107,24 +109,56 @@ int launch_cfg(dff_model* m, const ModelDev& M, const StepArgs& A, int grid, cud
     return DFF_OK;
 }
 
+// Launch policy.  Three configurations of the same kernel:
+//   wide : R = 64 rows, 1 head per chunk, 4-stage ring, 1 CTA/SM   (anything; the only one for N > 32)
+//   tall : R = 32 rows, 2 heads per chunk, 4-stage ring, 1 CTA/SM  (small batches: fewer, fatter phases)
+//   duo  : R = 32 rows, 1 head per chunk, 2-stage ring, <= 128 regs, 2 CTAs/SM (one CTA's tensor-core GEMMs overlap
+//          the other's CUDA-core phases)
+// DFF_CONFIG=wide|tall|duo overrides the choice (profiling).
 int launch(dff_model* m, StepArgs& A, cudaStream_t stream) {
     if (A.B <= 0) return DFF_OK;
     if (A.B > m->max_batch) return fail(DFF_EINVAL, "batch %d exceeds max_batch %d given to dff_model_create", A.B, m->max_batch);
     CUDA_TRY(cudaSetDevice(m->device));
     const int N = m->N;
     const int s64 = 64 / N, s32 = 32 / N;
-    const int need = (A.B + m->num_sms - 1) / m->num_sms;   // samples per CTA that cover the batch in one wave
-    int R, S;
-    if (s32 >= 1 && need <= s32) { R = 32; S = std::max(need, 1); }
-    else { R = 64; S = std::min(s64, std::max(need, 1)); }
-    const int ri = (R == 64) ? 1 : 0;
-    ModelDev M = m->md[ri];
+    enum { WIDE, TALL, DUO } cfg;
+    const int need1 = (A.B + m->num_sms - 1) / m->num_sms;            // samples per CTA covering the batch with 1 CTA/SM
+    const int need2 = (A.B + 2 * m->num_sms - 1) / (2 * m->num_sms);  // ... with 2 CTAs/SM
+    // measured on B200 (profiles/r01/ablation.md): tall wins when the batch fits one wave at R = 32 (C2: 2244 vs 1658 duo
+    // vs 1353 wide steps/s); duo wins for large batches when 32-row passes are as full as 64-row ones (C3: 269 vs 239
+    // wide); wide wins when a 32-row pass would be mostly padding (trp-cage N = 20: 239 vs 197 duo).
+    const bool rows32_full = s32 >= 1 && 2 * s32 * 10 >= s64 * 9;      // util(32) >= 0.9 * util(64)
+    if (s32 < 1) cfg = WIDE;
+    else if (need1 <= s32) cfg = TALL;
+    else if (rows32_full) cfg = DUO;
+    else cfg = WIDE;
+    if (const char* e = getenv("DFF_CONFIG")) {
+        if (!strcmp(e, "wide")) cfg = WIDE;
+        else if (!strcmp(e, "tall") && s32 >= 1) cfg = TALL;
+        else if (!strcmp(e, "duo") && s32 >= 1) cfg = DUO;
+    }
+    int R, S, ctas;
+    ModelDev M;
+    if (cfg == WIDE) { R = 64; S = std::min(s64, std::max(need1, 1)); M = m->md[1]; ctas = m->num_sms; }
+    else if (cfg == TALL) { R = 32; S = std::min(s32, std::max(need1, 1)); M = m->md[0]; ctas = m->num_sms; }
+    else {
+        R = 32; S = std::min(s32, std::max(need2, 1)); M = m->md[1]; ctas = 2 * m->num_sms;
+        M.layer_floats = m->layer_floats[0];
+        for (int i = 0; i < ST_COUNT; ++i) M.off[i] = m->off[0][i];
+    }
     M.S = S;
     const int n_groups = (A.B + S - 1) / S;
-    const int grid = std::min(n_groups, m->num_sms);
+    const int grid = std::min(n_groups, ctas);
+    if (grid > m->scratch_ctas) return fail(DFF_EINVAL, "internal: grid %d exceeds scratch slots %d", grid, m->scratch_ctas);
     m->last_R = R; m->last_S = S;
-    if (m->HP == 64) return (R == 64) ? launch_cfg<64, 64, 1>(m, M, A, grid, stream) : launch_cfg<64, 32, 2>(m, M, A, grid, stream);
-    return (R == 64) ? launch_cfg<128, 64, 1>(m, M, A, grid, stream) : launch_cfg<128, 32, 2>(m, M, A, grid, stream);
+    if (m->HP == 64) {
+        if (cfg == WIDE) return launch_cfg<Cfg<64, 64, 1>, 1>(m, M, A, grid, stream);
+        if (cfg == TALL) return launch_cfg<Cfg<64, 32, 2>, 1>(m, M, A, grid, stream);
+        return launch_cfg<Cfg<64, 32, 1, 2, 32>, 2>(m, M, A, grid, stream);
+    }
+    if (cfg == WIDE) return launch_cfg<Cfg<128, 64, 1>, 1>(m, M, A, grid, stream);
+    if (cfg == TALL) return launch_cfg<Cfg<128, 32, 2>, 1>(m, M, A, grid, stream);
+    return launch_cfg<Cfg<128, 32, 1, 2, 32>, 2>(m, M, A, grid, stream);
 }
 
 int ensure_io(dff_model* m, int slot, size_t floats) {
@@ -296,7 +330,8 @@ int dff_model_create(dff_model_t** out, int device, int num_beads, int hidden, i
     stash_geometry(32, m->NP, H, m->off[0], &m->layer_floats[0]);
     stash_geometry(64, m->NP, H, m->off[1], &m->layer_floats[1]);
     m->scratch_per_cta = (long long)L * m->layer_floats[1] + 64LL * H;
-    const int n_ctas = std::min(m->num_sms, std::max(1, max_batch));
+    const int n_ctas = std::min(2 * m->num_sms, std::max(1, max_batch));
+    m->scratch_ctas = n_ctas;
     if (cudaMalloc(&m->d_scratch, (size_t)n_ctas * m->scratch_per_cta * sizeof(float)) != cudaSuccess) { cleanup(); return fail(DFF_ENOMEM, "cudaMalloc scratch failed"); }
     if (cudaMalloc(&m->d_flags, sizeof(uint32_t)) != cudaSuccess) { cleanup(); return fail(DFF_ENOMEM, "cudaMalloc flags failed"); }
 

@@ -30,13 +30,14 @@ struct WStream {
     float* stage_base;
     uint64_t* full;       // [kStages] TMA completion (expect_tx) barriers
     uint32_t n;           // slices consumed so far (identical in every thread)
+    uint32_t nst, sh;     // ring depth (power of two) and its log2
     // producer cursor (meaningful in thread 0 only)
     const Seg* segs;      // segment table (a shared-memory copy when it fits)
     int nseg, seg_i;
     uint32_t slice_i, issued, total;
 
     __device__ __forceinline__ void issue_one() {
-        const uint32_t st = issued & (kStages - 1);
+        const uint32_t st = issued & (nst - 1);
         const Seg sg = segs[seg_i];
         mbar_expect_tx(full + st, sg.slice_bytes);
         bulk_g2s(stage_base + st * kStageFloats,
@@ -45,13 +46,13 @@ struct WStream {
         if (++slice_i == sg.n_slices) { slice_i = 0; if (++seg_i == nseg) seg_i = 0; }
     }
     __device__ __forceinline__ void prefill() {      // thread 0, once: nothing to wait for
-        for (int i = 0; i < kStages && issued < total; ++i) issue_one();
+        for (uint32_t i = 0; i < nst && issued < total; ++i) issue_one();
     }
     __device__ __forceinline__ const float* wait_slice() const {
-        mbar_wait(full + (n & (kStages - 1)), (n / kStages) & 1u);
-        return stage_base + (n & (kStages - 1)) * kStageFloats;
+        mbar_wait(full + (n & (nst - 1)), (n >> sh) & 1u);
+        return stage_base + (n & (nst - 1)) * kStageFloats;
     }
-    // All warps are done with the stage after the CTA barrier; thread 0 then refills it with slice n + kStages.
+    // All warps are done with the stage after the CTA barrier; thread 0 then refills it with slice n + nst.
     // (A warp-granular full/empty mbarrier hand-off was measured and was not faster: profiles/r01/ablation.md.)
     __device__ __forceinline__ void release_slice() {
         __syncthreads();
@@ -302,8 +303,11 @@ __device__ __forceinline__ void attn_pv(const float* sPm, int ldp_head, int NP, 
 }
 
 // ------------------------------------------------------------------ configuration
-template <int HP, int R, int HC>
+template <int HP, int R, int HC, int NS = kStages, int PN = kMaxBeads>
 struct Cfg {
+    static constexpr int kHP = HP, kR = R, kHC = HC;
+    static constexpr int kNumStages = NS;    // weight-ring depth
+    static constexpr int kPN = PN;           // largest padded bead count this configuration accepts
     static constexpr int CWQ = 64 * HC;      // q / k' / v' tile width of one head chunk
     static constexpr int NCH = kHeads / HC;  // head chunks per layer
     static constexpr int LDH = HP + 4;       // [R][HP] activation buffers
@@ -311,7 +315,7 @@ struct Cfg {
     static constexpr int LDO = CWQ + 4;      // attention output of the chunk / its gradient
     static constexpr int LDF = 128 + 4;      // FF hidden chunk (aliases the qkv buffer)
     static constexpr int EPL = HP / 32;      // columns per lane in warp-per-row phases
-    static constexpr int PSZ = HC * R * kMaxBeads;   // attention probabilities of the chunk [HC][R][NP]
+    static constexpr int PSZ = HC * R * PN;          // attention probabilities of the chunk [HC][R][NP]
     // shared memory carve-up (float offsets)
     static constexpr int oN = 0;
     static constexpr int oNh = oN + R * LDH;
@@ -320,13 +324,13 @@ struct Cfg {
     static constexpr int oP = oO + R * LDO;
     static constexpr int oDS = oP + PSZ;
     static constexpr int oW = oDS + PSZ;
-    static constexpr int oX = oW + kStages * kStageFloats;
+    static constexpr int oX = oW + NS * kStageFloats;
     static constexpr int oV = oX + R * 4;
     static constexpr int oDX = oV + R * 4;
     static constexpr int oTmp = oDX + R * 4;
     static constexpr int oSeg = oTmp + R * 4;
     static constexpr int oBar = oSeg + kSegCap * 4;
-    static constexpr int kFloats = oBar + 2 * kStages;
+    static constexpr int kFloats = oBar + 2 * NS;
     static constexpr size_t kSmemBytes = (size_t)kFloats * sizeof(float);
     static_assert(LDQ >= LDF, "FF chunk buffer must fit in the qkv buffer");
 };
@@ -364,10 +368,10 @@ __device__ __forceinline__ void stash_load_async(float* __restrict__ dst, int ld
 
 // ------------------------------------------------------------------ warp-per-row phases
 // LayerNorm of sN rows -> sNh, stats (mean, rstd) -> global; optionally stashes the input rows.
-template <int HP, int R, int HC>
+template <class C>
 __device__ __forceinline__ void ln_forward_rows(const float* sN, float* sNh, const float* __restrict__ gam,
                                                 const float* __restrict__ bet, int H, float* st_rows, float* st_stats) {
-    using C = Cfg<HP, R, HC>;
+    constexpr int R = C::kR;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int r = warp; r < R; r += kWarps) {
         float x[C::EPL];
@@ -403,12 +407,12 @@ __device__ __forceinline__ void ln_forward_rows(const float* sN, float* sNh, con
 
 // GatedResidual forward (graph_transformer.py:202-205) on rows: a = sNh, n = sN -> out -> sN,
 // then (if gam) LayerNorm(out) -> sNh.  Stashes a, gate, out (and LN stats).
-template <int HP, int R, int HC>
+template <class C>
 __device__ __forceinline__ void gate_ln_forward_rows(float* sN, float* sNh, const float* __restrict__ ga,
                                                      const float* __restrict__ gb, int H, float* st_a, float* st_g,
                                                      float* st_out, const float* __restrict__ gam,
                                                      const float* __restrict__ bet, float* st_stats) {
-    using C = Cfg<HP, R, HC>;
+    constexpr int R = C::kR;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int r = warp; r < R; r += kWarps) {
         float a[C::EPL], n[C::EPL], o[C::EPL];
@@ -460,12 +464,12 @@ __device__ __forceinline__ void gate_ln_forward_rows(float* sN, float* sNh, cons
 // Reverse of [LayerNorm ->] GatedResidual on rows.
 //   dout = sN (+ LN-backward of sNh through (st_ln_in, stats, gam) when gam != nullptr)
 //   d(gate input a) -> sNh,  d(residual n) -> sN.      a, n, g come from the stash.
-template <int HP, int R, int HC>
+template <class C>
 __device__ __forceinline__ void gate_backward_rows(float* sN, float* sNh, int H, const float* __restrict__ gam,
                                                    const float* st_ln_in, const float* st_stats, const float* st_a,
                                                    const float* st_n, const float* st_g, const float* __restrict__ ga,
                                                    const float* __restrict__ gb) {
-    using C = Cfg<HP, R, HC>;
+    constexpr int R = C::kR;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int r = warp; r < R; r += kWarps) {
         float d[C::EPL], a[C::EPL], n[C::EPL];
@@ -516,10 +520,10 @@ __device__ __forceinline__ void gate_backward_rows(float* sN, float* sNh, int H,
 }
 
 // sN += LayerNorm-backward(sNh) through (st_ln_in, stats, gam)
-template <int HP, int R, int HC>
+template <class C>
 __device__ __forceinline__ void ln_backward_rows(float* sN, const float* sNh, int H, const float* __restrict__ gam,
                                                  const float* st_ln_in, const float* st_stats) {
-    using C = Cfg<HP, R, HC>;
+    constexpr int R = C::kR;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int r = warp; r < R; r += kWarps) {
         const float mean = st_stats[r * 2], rstd = st_stats[r * 2 + 1];
@@ -615,9 +619,9 @@ __device__ __forceinline__ void softmax_backward_rows(float* sDS, const float* s
 }
 
 // ------------------------------------------------------------------ forward pass (energy) for one group of samples
-template <int HP, int R, int HC>
+template <class C>
 __device__ void forward_pass(const ModelDev& M, Ctx& c, float t_norm) {
-    using C = Cfg<HP, R, HC>;
+    constexpr int HP = C::kHP, R = C::kR, HC = C::kHC;
     const int tid = threadIdx.x;
     const int N = M.N, NP = M.NP, H = M.H;
 
@@ -629,7 +633,7 @@ __device__ void forward_pass(const ModelDev& M, Ctx& c, float t_norm) {
         c.sN[r * C::LDH + d] = v;
     }
     __syncthreads();
-    ln_forward_rows<HP, R, HC>(c.sN, c.sNh, M.layer[0].ln1_g, M.layer[0].ln1_b, H, c.stash + M.off[ST_NIN],
+    ln_forward_rows<C>(c.sN, c.sNh, M.layer[0].ln1_g, M.layer[0].ln1_b, H, c.stash + M.off[ST_NIN],
                                c.stash + M.off[ST_STAT1]);
     __syncthreads();
 
@@ -695,7 +699,7 @@ __device__ void forward_pass(const ModelDev& M, Ctx& c, float t_norm) {
         });
         __syncthreads();
         // gated residual 1 + LayerNorm 2
-        gate_ln_forward_rows<HP, R, HC>(c.sN, c.sNh, W.g1a, W.g1b, H, st + M.off[ST_ATT], st + M.off[ST_G1],
+        gate_ln_forward_rows<C>(c.sN, c.sNh, W.g1a, W.g1b, H, st + M.off[ST_ATT], st + M.off[ST_G1],
                                         st + M.off[ST_M], W.ln2_g, W.ln2_b, st + M.off[ST_STAT2]);
         __syncthreads();
         // feed-forward, 128 hidden columns at a time
@@ -723,7 +727,7 @@ __device__ void forward_pass(const ModelDev& M, Ctx& c, float t_norm) {
         // gated residual 2 (+ next layer's LayerNorm 1; its input rows are the next layer's n_in stash)
         const bool last = (l + 1 == M.L);
         float* stn = st + M.layer_floats;
-        gate_ln_forward_rows<HP, R, HC>(c.sN, c.sNh, W.g2a, W.g2b, H, st + M.off[ST_FF], st + M.off[ST_G2],
+        gate_ln_forward_rows<C>(c.sN, c.sNh, W.g2a, W.g2b, H, st + M.off[ST_FF], st + M.off[ST_G2],
                                         stn + M.off[ST_NIN],
                                         last ? nullptr : M.layer[l + 1].ln1_g, last ? nullptr : M.layer[l + 1].ln1_b,
                                         last ? nullptr : stn + M.off[ST_STAT1]);
@@ -732,9 +736,9 @@ __device__ void forward_pass(const ModelDev& M, Ctx& c, float t_norm) {
 }
 
 // ------------------------------------------------------------------ reverse pass: sDX[r][0..2] = d sum(E) / d x_r
-template <int HP, int R, int HC>
+template <class C>
 __device__ void backward_pass(const ModelDev& M, Ctx& c) {
-    using C = Cfg<HP, R, HC>;
+    constexpr int HP = C::kHP, R = C::kR, HC = C::kHC;
     const int tid = threadIdx.x;
     const int N = M.N, NP = M.NP, H = M.H;
 
@@ -750,7 +754,7 @@ __device__ void backward_pass(const ModelDev& M, Ctx& c) {
         float* st = c.stash + (size_t)l * M.layer_floats;
 
         // gated residual 2 backward: d ff -> sNh, d m (partial) -> sN
-        gate_backward_rows<HP, R, HC>(c.sN, c.sNh, H, nullptr, nullptr, nullptr, st + M.off[ST_FF], st + M.off[ST_M],
+        gate_backward_rows<C>(c.sN, c.sNh, H, nullptr, nullptr, nullptr, st + M.off[ST_FF], st + M.off[ST_M],
                                       st + M.off[ST_G2], W.g2a, W.g2b);
         __syncthreads();
         // feed-forward backward
@@ -778,7 +782,7 @@ __device__ void backward_pass(const ModelDev& M, Ctx& c) {
         });
         __syncthreads();
         // LayerNorm 2 backward + gated residual 1 backward: d att -> sNh, d n_in (residual part) -> sN
-        gate_backward_rows<HP, R, HC>(c.sN, c.sNh, H, W.ln2_g, st + M.off[ST_M], st + M.off[ST_STAT2], st + M.off[ST_ATT],
+        gate_backward_rows<C>(c.sN, c.sNh, H, W.ln2_g, st + M.off[ST_M], st + M.off[ST_STAT2], st + M.off[ST_ATT],
                                       st + M.off[ST_NIN], st + M.off[ST_G1], W.g1a, W.g1b);
         __syncthreads();
 
@@ -861,17 +865,17 @@ __device__ void backward_pass(const ModelDev& M, Ctx& c) {
                 *reinterpret_cast<float2*>(c.sNh + row * C::LDH + col) = make_float2(v0, v1);
             });
             __syncthreads();
-            ln_backward_rows<HP, R, HC>(c.sN, c.sNh, H, W.ln1_g, st + M.off[ST_NIN], st + M.off[ST_STAT1]);
+            ln_backward_rows<C>(c.sN, c.sNh, H, W.ln1_g, st + M.off[ST_NIN], st + M.off[ST_STAT1]);
             __syncthreads();
         }
     }
 }
 
 // ------------------------------------------------------------------ the kernel
-template <int HP, int R, int HC>
-__global__ void __launch_bounds__(kThreads, 1)
+template <class C, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
 dff_fused_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ StepArgs A) {
-    using C = Cfg<HP, R, HC>;
+    constexpr int R = C::kR;
     extern __shared__ __align__(128) float smem[];
     const int tid = threadIdx.x;
     const int N = M.N;
@@ -889,6 +893,8 @@ dff_fused_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ Ste
     c.ws.stage_base = smem + C::oW;
     c.ws.full = reinterpret_cast<uint64_t*>(smem + C::oBar);
     c.ws.n = 0;
+    c.ws.nst = C::kNumStages;
+    c.ws.sh = (C::kNumStages == 4) ? 2u : 1u;
     c.ws.nseg = A.need_backward ? M.nseg_all : M.nseg_fwd;
     c.ws.segs = M.segs;
     if (c.ws.nseg <= kSegCap) {      // keep the producer's table off the global-memory critical path
@@ -899,7 +905,7 @@ dff_fused_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ Ste
     c.ws.seg_i = 0; c.ws.slice_i = 0; c.ws.issued = 0;
     c.ws.total = (uint32_t)my_groups * (uint32_t)A.n_steps * (A.need_backward ? M.nslice_all : M.nslice_fwd);
     if (tid == 0) {
-        for (int i = 0; i < kStages; ++i) mbar_init(c.ws.full + i, 1);
+        for (int i = 0; i < C::kNumStages; ++i) mbar_init(c.ws.full + i, 1);
         fence_barrier_init();
     }
     for (int idx = tid; idx < C::oW; idx += kThreads) smem[idx] = 0.f;       // activations / attention buffers
@@ -934,7 +940,7 @@ dff_fused_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ Ste
             const int it = A.t_start - step;
             const float t_norm = (A.mode == MODE_DDPM) ? (float)it / (float)A.T : A.t_norm;
 
-            forward_pass<HP, R, HC>(M, c, t_norm);
+            forward_pass<C>(M, c, t_norm);
             if (A.energy_out != nullptr) {   // node_decoder (graph_transformer.py:106)
                 const int lane = tid & 31, warp = tid >> 5;
                 for (int r = warp; r < c.rows_act; r += kWarps) {
@@ -945,7 +951,7 @@ dff_fused_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ Ste
                 }
             }
             __syncthreads();
-            if (A.need_backward) backward_pass<HP, R, HC>(M, c);
+            if (A.need_backward) backward_pass<C>(M, c);
             __syncthreads();
 
             if (A.mode == MODE_SCORE) {
