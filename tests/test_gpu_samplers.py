@@ -129,3 +129,50 @@ def test_device_rng_statistics():
     eng.langevin_steps(x_b, None, 1, prm, torch.ones(N, device="cuda"), seed=7)
     eng.langevin_steps(x_c, None, 1, prm, torch.ones(N, device="cuda"), seed=8)
     assert torch.equal(x_a, x_b) and not torch.equal(x_a, x_c)
+
+
+def test_ddpm_flags_clamp_and_centre():
+    """The reference's per-step host checks became device flags: +-1000 clamp (ddpm.py:248-250) and the centre assertion
+    (utils.py:73-86)."""
+    from dff_b200 import _native as nat
+    eng = _engine(net_params("ala2_fold1"))
+    sched = _sched_dev("ala2_fold1")
+    x = torch.zeros(2, 5, 3, device="cuda")
+    x[0, 0, 0], x[0, 1, 0] = 4000.0, -4000.0                 # centred but far outside the clamp
+    eng.read_flags()
+    eng.ddpm_steps(x, 10, 1, 1000, sched, noise=torch.zeros(1, 2, 5, 3, device="cuda"))
+    f = eng.read_flags()
+    assert f & nat.FLAG_CLAMPED and float(x.abs().max()) <= 1000.0 + 1e-3
+    y = torch.ones(2, 5, 3, device="cuda")                   # centroid at (1,1,1): violates assert_center_zero on entry
+    eng.ddpm_steps(y, 10, 1, 1000, sched, noise=torch.zeros(1, 2, 5, 3, device="cuda"))
+    assert eng.read_flags() & nat.FLAG_CENTER
+    assert float(y.mean(1).abs().max()) < 1e-4               # and the step still re-centres (ddpm.py:251)
+
+
+def test_host_buffer_entry_points_match_device_path():
+    """dff_score_host / dff_langevin_run_host (the e2e path bench.py times) == the device-pointer path."""
+    import ctypes as C
+    from dff_b200 import _native as nat
+    mol = "chignolin"
+    g = load(f"langevin_{mol}.pt")
+    r = g["runs"][0]
+    std = g["meta"]["std"]
+    eng = _engine(net_params(mol))
+    prm = _md_params(schedule(mol), std, r)
+    x0 = (r["init_mol"] / std).contiguous()
+    B, N = x0.shape[:2]
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    eps_h = torch.empty_like(x0); en_h = torch.empty(B, N)
+    nat.check(nat.lib().dff_score_host(eng._h, vp(x0), 0.02, B, vp(eps_h), vp(en_h)))
+    eps_d, en_d = eng.score(x0.cuda(), 0.02, want_energy=True)
+    assert torch.equal(eps_h, eps_d.cpu()) and torch.equal(en_h, en_d.cpu())
+    xh, vh = x0.clone(), torch.zeros_like(x0)
+    fh, kh = torch.empty(3, B, N, 3), torch.empty(3, B)
+    flg = torch.zeros(1, dtype=torch.int32)
+    mass = torch.tensor(r["masses"], dtype=torch.float32)
+    nat.check(nat.lib().dff_langevin_run_host(eng._h, vp(xh), vp(vh), B, 12, C.byref(prm), vp(mass), 77, 4, vp(fh), vp(kh), vp(flg)))
+    xd, vd = x0.cuda(), torch.zeros_like(x0).cuda()
+    fd, kd = torch.empty(3, B, N, 3, device="cuda"), torch.empty(3, B, device="cuda")
+    eng.langevin_steps(xd, vd, 12, prm, mass.cuda(), noise=None, seed=77, offset=0, save_interval=4, frames=fd, ke=kd)
+    assert torch.equal(xh, xd.cpu()) and torch.equal(vh, vd.cpu()) and torch.equal(fh, fd.cpu()) and torch.equal(kh, kd.cpu())
+    assert torch.isfinite(fh).all()

@@ -64,3 +64,51 @@ def test_invariants_translation_and_zero_net_force():
     f1, _ = eng.score((x + torch.tensor([1.5, -2.0, 0.25], device="cuda")).contiguous(), 0.02)
     assert rel_err(f1, f0) < 1e-5                                   # center_zero inside forward (graph_transformer.py:87)
     assert float(f0.sum(1).abs().max()) < 1e-3 * float(f0.abs().max())   # sum_i F_i = 0
+
+
+@pytest.mark.parametrize("N,H,L,B", [(2, 32, 1, 1), (3, 64, 1, 5), (16, 96, 2, 9), (33, 64, 2, 4), (64, 32, 1, 3)])
+def test_unusual_shapes_vs_oracle(N, H, L, B):
+    """Shapes no checkpoint uses (smallest/largest N, H = 32, a single layer) against the fp64 collapsed oracle
+    and the literal fp32 oracle."""
+    from oracle import collapsed_ref, score_ref
+    from oracle.weights import synthetic_net_params
+    p = synthetic_net_params(N, H, L, seed=100 + N)
+    eng = _engine(p)
+    g = torch.Generator().manual_seed(N)
+    x = torch.randn(B, N, 3, generator=g)
+    f64, e64, _ = collapsed_ref.forward_backward(score_ref.to_dtype(p, torch.float64), x.double(), 0.4)
+    eps, en = eng.score(x.cuda(), 0.4, want_energy=True)
+    assert rel_err(eps, f64) < FORCE_RTOL and rel_err(en, e64) < FORCE_RTOL
+    assert rel_err(eps, score_ref.score_forward(p, x, 0.4)) < FORCE_RTOL
+
+
+def test_deterministic_and_config_independent(monkeypatch):
+    """Bitwise repeatable; and the three launch configurations agree to fp32 rounding."""
+    p = net_params("chignolin")
+    x = load("score_chignolin.pt")["cases"][1]["x"].cuda().contiguous()
+    eng = _engine(p)
+    a, _ = eng.score(x, 0.005)
+    b, _ = eng.score(x, 0.005)
+    assert torch.equal(a, b)
+    outs = {}
+    for cfg in ("wide", "tall", "duo"):
+        monkeypatch.setenv("DFF_CONFIG", cfg)
+        outs[cfg], _ = eng.score(x, 0.005)
+    assert rel_err(outs["tall"], outs["wide"]) < 2e-5 and rel_err(outs["duo"], outs["wide"]) < 2e-5
+
+
+def test_abi_error_behaviour():
+    from dff_b200 import DffError, ScoreEngine
+    from oracle.weights import synthetic_net_params
+    eng = _engine(net_params("ala2_fold1"), max_batch=4)
+    with pytest.raises(DffError, match="max_batch"):
+        eng.score(torch.zeros(5, 5, 3, device="cuda"), 0.1)
+    with pytest.raises(DffError):
+        ScoreEngine(synthetic_net_params(65, 64, 1), device="cuda:0")              # N > 64
+    with pytest.raises(DffError):
+        ScoreEngine(synthetic_net_params(5, 80, 1), device="cuda:0")               # hidden not a multiple of 32
+    with pytest.raises(DffError):
+        eng.score(torch.zeros(2, 5, 3), 0.1)                                       # host tensor: no silent CPU path
+    bad = synthetic_net_params(5, 64, 1, in_edge=1)
+    with pytest.raises(DffError, match="intrinsic"):
+        ScoreEngine(bad, device="cuda:0")

@@ -274,7 +274,7 @@ int dff_model_create(dff_model_t** out, int device, int num_beads, int hidden, i
             const size_t o = P.alloc((size_t)K * NCP);
             for (int k = 0; k < K; ++k)
                 for (int c2 = 0; c2 < NC; ++c2) P.buf[o + (size_t)k * NCP + c2] = fill(k, c2);
-            const int KS = ks_for(NC);
+            const int KS = ks_for(NC);     // must equal gemm_acc's KS (slice multiplier KM = 1 in every shipped configuration)
             segs[ci].push_back({o, (uint32_t)(KS * NCP * sizeof(float)), (uint32_t)(K / KS)});
         };
         for (int l = 0; l < L; ++l) {

@@ -31,6 +31,7 @@ struct WStream {
     uint64_t* full;       // [kStages] TMA completion (expect_tx) barriers
     uint32_t n;           // slices consumed so far (identical in every thread)
     uint32_t nst, sh;     // ring depth (power of two) and its log2
+    uint32_t stage_floats;
     // producer cursor (meaningful in thread 0 only)
     const Seg* segs;      // segment table (a shared-memory copy when it fits)
     int nseg, seg_i;
@@ -40,7 +41,7 @@ struct WStream {
         const uint32_t st = issued & (nst - 1);
         const Seg sg = segs[seg_i];
         mbar_expect_tx(full + st, sg.slice_bytes);
-        bulk_g2s(stage_base + st * kStageFloats,
+        bulk_g2s(stage_base + st * stage_floats,
                  reinterpret_cast<const char*>(sg.base) + (size_t)slice_i * sg.slice_bytes, sg.slice_bytes, full + st);
         ++issued;
         if (++slice_i == sg.n_slices) { slice_i = 0; if (++seg_i == nseg) seg_i = 0; }
@@ -50,7 +51,7 @@ struct WStream {
     }
     __device__ __forceinline__ const float* wait_slice() const {
         mbar_wait(full + (n & (nst - 1)), (n >> sh) & 1u);
-        return stage_base + (n & (nst - 1)) * kStageFloats;
+        return stage_base + (n & (nst - 1)) * stage_floats;
     }
     // All warps are done with the stage after the CTA barrier; thread 0 then refills it with slice n + nst.
     // (A warp-granular full/empty mbarrier hand-off was measured and was not faster: profiles/r01/ablation.md.)
@@ -108,12 +109,12 @@ struct Acc {
     }
 };
 
-template <int R, int CW, int NT>
+template <int R, int CW, int NT, int KM = 1>
 __device__ __forceinline__ void gemm_acc(WStream& ws, const float* __restrict__ sA, int lda, int K, Acc<R, CW, NT>& acc) {
     using A_ = Acc<R, CW, NT>;
     constexpr int NC = CW * NT;
     constexpr int NCP = NC + kWPad;
-    constexpr int KS = (NC == 384) ? 8 : (NC == 192 ? 16 : (NC == 128 ? 16 : 32));
+    constexpr int KS = ((NC == 384) ? 8 : (NC == 192 ? 16 : (NC == 128 ? 16 : 32))) * (NC == 64 ? 1 : KM);   // rows per streamed slice
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wr = warp >> 2, wc = warp & 3;
     const int g = lane >> 2, tig = lane & 3;
@@ -277,16 +278,37 @@ __device__ __forceinline__ void attn_pv_t(const float* __restrict__ sPm, int ldp
         for (int a = 0; a < TI; ++a) acc[a] = make_float4(0.f, 0.f, 0.f, 0.f);
         const float* bp = sB + (s * N) * ldb + hh * 64 + dg * 4;
         const float* pp = sPm + hh * ldp_head + (s * N) * NP;
+        if (TRANS) {
 #pragma unroll 2
-        for (int j = 0; j < N; ++j) {
-            const float4 b = *reinterpret_cast<const float4*>(bp + j * ldb);
+            for (int j = 0; j < N; ++j) {
+                const float4 b = *reinterpret_cast<const float4*>(bp + j * ldb);
 #pragma unroll
-            for (int a = 0; a < TI; ++a) {
-                const float pv = TRANS ? pp[j * NP + rows[a]] : pp[rows[a] * NP + j];
-                acc[a].x = fmaf(pv, b.x, acc[a].x);
-                acc[a].y = fmaf(pv, b.y, acc[a].y);
-                acc[a].z = fmaf(pv, b.z, acc[a].z);
-                acc[a].w = fmaf(pv, b.w, acc[a].w);
+                for (int a = 0; a < TI; ++a) {
+                    const float pv = pp[j * NP + rows[a]];
+                    acc[a].x = fmaf(pv, b.x, acc[a].x);
+                    acc[a].y = fmaf(pv, b.y, acc[a].y);
+                    acc[a].z = fmaf(pv, b.z, acc[a].z);
+                    acc[a].w = fmaf(pv, b.w, acc[a].w);
+                }
+            }
+        } else {
+            // rows of P are padded to NP (multiple of 4) with zeros: one 16-byte load covers 4 values of j
+            for (int j = 0; j < N; j += 4) {
+                float4 p4[TI];
+#pragma unroll
+                for (int a = 0; a < TI; ++a) p4[a] = *reinterpret_cast<const float4*>(pp + rows[a] * NP + j);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float4 b = *reinterpret_cast<const float4*>(bp + min(j + u, N - 1) * ldb);   // pad columns carry p = 0
+#pragma unroll
+                    for (int a = 0; a < TI; ++a) {
+                        const float pv = (u == 0) ? p4[a].x : (u == 1) ? p4[a].y : (u == 2) ? p4[a].z : p4[a].w;
+                        acc[a].x = fmaf(pv, b.x, acc[a].x);
+                        acc[a].y = fmaf(pv, b.y, acc[a].y);
+                        acc[a].z = fmaf(pv, b.z, acc[a].z);
+                        acc[a].w = fmaf(pv, b.w, acc[a].w);
+                    }
+                }
             }
         }
 #pragma unroll
@@ -303,8 +325,9 @@ __device__ __forceinline__ void attn_pv(const float* sPm, int ldp_head, int NP, 
 }
 
 // ------------------------------------------------------------------ configuration
-template <int HP, int R, int HC, int NS = kStages, int PN = kMaxBeads>
+template <int HP, int R, int HC, int NS = kStages, int PN = kMaxBeads, int KM = 1>
 struct Cfg {
+    static constexpr int kKM = KM;           // weight-slice size multiplier (stage = KM * 12.5 KB)
     static constexpr int kHP = HP, kR = R, kHC = HC;
     static constexpr int kNumStages = NS;    // weight-ring depth
     static constexpr int kPN = PN;           // largest padded bead count this configuration accepts
@@ -324,7 +347,7 @@ struct Cfg {
     static constexpr int oP = oO + R * LDO;
     static constexpr int oDS = oP + PSZ;
     static constexpr int oW = oDS + PSZ;
-    static constexpr int oX = oW + NS * kStageFloats;
+    static constexpr int oX = oW + NS * KM * kStageFloats;
     static constexpr int oV = oX + R * 4;
     static constexpr int oDX = oV + R * 4;
     static constexpr int oTmp = oDX + R * 4;
@@ -647,7 +670,7 @@ __device__ void forward_pass(const ModelDev& M, Ctx& c, float t_norm) {
             {   // q | k | v of the head chunk:  n_hat [R][H] x Wqkv_f[l][hc] [H][3*CWQ]
                 Acc<R, C::CWQ, 3> acc;
                 acc.zero();
-                gemm_acc<R, C::CWQ, 3>(c.ws, c.sNh, C::LDH, H, acc);
+                gemm_acc<R, C::CWQ, 3, C::kKM>(c.ws, c.sNh, C::LDH, H, acc);
                 tile_foreach<R, C::CWQ, 3>(acc, [&](int t, int, int, int, int row, int col, float v0, float v1) {
                     const float2 b = __ldg(reinterpret_cast<const float2*>(W.bqkv + hc * 3 * C::CWQ + t * C::CWQ + col));
                     float o[2] = {v0 + b.x, v1 + b.y};
@@ -691,7 +714,7 @@ __device__ void forward_pass(const ModelDev& M, Ctx& c, float t_norm) {
             });
             __syncthreads();
             // att += o_chunk [R][CWQ] x Wo_f[l][hc] [CWQ][HP]
-            gemm_acc<R, HP, 1>(c.ws, c.sO, C::LDO, C::CWQ, acc_a);
+            gemm_acc<R, HP, 1, C::kKM>(c.ws, c.sO, C::LDO, C::CWQ, acc_a);
         }
         tile_foreach<R, HP, 1>(acc_a, [&](int, int, int, int, int row, int col, float v0, float v1) {
             const float2 b = __ldg(reinterpret_cast<const float2*>(W.bo + col));
@@ -709,7 +732,7 @@ __device__ void forward_pass(const ModelDev& M, Ctx& c, float t_norm) {
         for (int ch = 0; ch < M.nch; ++ch) {
             Acc<R, 128, 1> acc1;
             acc1.zero();
-            gemm_acc<R, 128, 1>(c.ws, c.sNh, C::LDH, H, acc1);
+            gemm_acc<R, 128, 1, C::kKM>(c.ws, c.sNh, C::LDH, H, acc1);
             tile_foreach<R, 128, 1>(acc1, [&](int, int, int, int, int row, int col, float v0, float v1) {
                 const float2 b = __ldg(reinterpret_cast<const float2*>(W.b1 + ch * 128 + col));
                 const float2 pre = make_float2(v0 + b.x, v1 + b.y);
@@ -717,7 +740,7 @@ __device__ void forward_pass(const ModelDev& M, Ctx& c, float t_norm) {
                 *reinterpret_cast<float2*>(sH1 + row * C::LDF + col) = make_float2(gelu_f(pre.x), gelu_f(pre.y));
             });
             __syncthreads();
-            gemm_acc<R, HP, 1>(c.ws, sH1, C::LDF, 128, acc_f);
+            gemm_acc<R, HP, 1, C::kKM>(c.ws, sH1, C::LDF, 128, acc_f);
         }
         tile_foreach<R, HP, 1>(acc_f, [&](int, int, int, int, int row, int col, float v0, float v1) {
             const float2 b = __ldg(reinterpret_cast<const float2*>(W.b2 + col));
@@ -769,13 +792,13 @@ __device__ void backward_pass(const ModelDev& M, Ctx& c) {
             tile_foreach<R, 128, 1>(acc1, [&](int, int m, int n, int half, int row, int col, float, float) {
                 pre[m][n][half] = *reinterpret_cast<const float2*>(st + M.off[ST_H1] + (size_t)row * (4 * H) + ch * 128 + col);
             });
-            gemm_acc<R, 128, 1>(c.ws, c.sNh, C::LDH, H, acc1);          // d act = d ff x W2_b[ch]
+            gemm_acc<R, 128, 1, C::kKM>(c.ws, c.sNh, C::LDH, H, acc1);          // d act = d ff x W2_b[ch]
             tile_foreach<R, 128, 1>(acc1, [&](int, int m, int n, int half, int row, int col, float v0, float v1) {
                 *reinterpret_cast<float2*>(sH1 + row * C::LDF + col) =
                     make_float2(v0 * gelu_grad_f(pre[m][n][half].x), v1 * gelu_grad_f(pre[m][n][half].y));
             });
             __syncthreads();
-            gemm_acc<R, HP, 1>(c.ws, sH1, C::LDF, 128, acc_dm);            // d m_hat += d h1 x W1_b[ch]
+            gemm_acc<R, HP, 1, C::kKM>(c.ws, sH1, C::LDF, 128, acc_dm);            // d m_hat += d h1 x W1_b[ch]
         }
         tile_foreach<R, HP, 1>(acc_dm, [&](int, int, int, int, int row, int col, float v0, float v1) {
             *reinterpret_cast<float2*>(c.sNh + row * C::LDH + col) = make_float2(v0, v1);
@@ -798,7 +821,7 @@ __device__ void backward_pass(const ModelDev& M, Ctx& c) {
             {   // d o_chunk = d att x Wo_b[l][hc]   [R][H] x [H][CWQ]
                 Acc<R, C::CWQ, 1> acc;
                 acc.zero();
-                gemm_acc<R, C::CWQ, 1>(c.ws, c.sNh, C::LDH, H, acc);
+                gemm_acc<R, C::CWQ, 1, C::kKM>(c.ws, c.sNh, C::LDH, H, acc);
                 tile_foreach<R, C::CWQ, 1>(acc, [&](int, int, int, int, int row, int col, float v0, float v1) {
                     *reinterpret_cast<float2*>(c.sO + row * C::LDO + col) = make_float2(v0, v1);
                 });
@@ -855,7 +878,7 @@ __device__ void backward_pass(const ModelDev& M, Ctx& c) {
                 c.sDX[r * 4 + cc] += s;
             }
             if (l > 0) {   // d n_hat += [dv' | dk' | dq] [R][3*CWQ] x Wqkv_b[l][hc] [3*CWQ][HP]
-                gemm_acc<R, HP, 1>(c.ws, c.sQKV, C::LDQ, 3 * C::CWQ, acc_dn);
+                gemm_acc<R, HP, 1, C::kKM>(c.ws, c.sQKV, C::LDQ, 3 * C::CWQ, acc_dn);
             } else {
                 __syncthreads();
             }
@@ -894,6 +917,7 @@ dff_fused_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ Ste
     c.ws.full = reinterpret_cast<uint64_t*>(smem + C::oBar);
     c.ws.n = 0;
     c.ws.nst = C::kNumStages;
+    c.ws.stage_floats = C::kKM * kStageFloats;
     c.ws.sh = (C::kNumStages == 4) ? 2u : 1u;
     c.ws.nseg = A.need_backward ? M.nseg_all : M.nseg_fwd;
     c.ws.segs = M.segs;
