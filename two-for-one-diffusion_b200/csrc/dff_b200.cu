@@ -130,12 +130,12 @@ int launch(dff_model* m, StepArgs& A, cudaStream_t stream) {
     const bool rows32_full = s32 >= 1 && 2 * s32 * 10 >= s64 * 9;      // util(32) >= 0.9 * util(64)
     if (s32 < 1) cfg = WIDE;
     else if (need1 <= s32) cfg = TALL;
-    else if (rows32_full) cfg = DUO;
+    else if (rows32_full && kThreads == 256) cfg = DUO;
     else cfg = WIDE;
     if (const char* e = getenv("DFF_CONFIG")) {
         if (!strcmp(e, "wide")) cfg = WIDE;
         else if (!strcmp(e, "tall") && s32 >= 1) cfg = TALL;
-        else if (!strcmp(e, "duo") && s32 >= 1) cfg = DUO;
+        else if (!strcmp(e, "duo") && s32 >= 1 && kThreads == 256) cfg = DUO;
     }
     int R, S, ctas;
     ModelDev M;
@@ -150,15 +150,19 @@ int launch(dff_model* m, StepArgs& A, cudaStream_t stream) {
     const int n_groups = (A.B + S - 1) / S;
     const int grid = std::min(n_groups, ctas);
     if (grid > m->scratch_ctas) return fail(DFF_EINVAL, "internal: grid %d exceeds scratch slots %d", grid, m->scratch_ctas);
+    {   // the in-kernel weight-slice counter is 32-bit: refuse launches that would overflow it
+        const double slices = (double)((n_groups + grid - 1) / grid) * (double)A.n_steps * (double)(A.need_backward ? M.nslice_all : M.nslice_fwd);
+        if (slices >= 4.0e9) return fail(DFF_EINVAL, "n_steps %d too large for one launch; split the call (e.g. per save interval)", A.n_steps);
+    }
     m->last_R = R; m->last_S = S;
     if (m->HP == 64) {
         if (cfg == WIDE) return launch_cfg<Cfg<64, 64, 1>, 1>(m, M, A, grid, stream);
         if (cfg == TALL) return launch_cfg<Cfg<64, 32, 2>, 1>(m, M, A, grid, stream);
-        return launch_cfg<Cfg<64, 32, 1, 2, 32>, 2>(m, M, A, grid, stream);
+        return launch_cfg<Cfg<64, 32, 1, 2, 32>, (kThreads == 256 ? 2 : 1)>(m, M, A, grid, stream);
     }
     if (cfg == WIDE) return launch_cfg<Cfg<128, 64, 1>, 1>(m, M, A, grid, stream);
     if (cfg == TALL) return launch_cfg<Cfg<128, 32, 2>, 1>(m, M, A, grid, stream);
-    return launch_cfg<Cfg<128, 32, 1, 2, 32>, 2>(m, M, A, grid, stream);
+    return launch_cfg<Cfg<128, 32, 1, 2, 32>, (kThreads == 256 ? 2 : 1)>(m, M, A, grid, stream);
 }
 
 int ensure_io(dff_model* m, int slot, size_t floats) {

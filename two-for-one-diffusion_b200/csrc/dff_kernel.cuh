@@ -67,8 +67,8 @@ struct WStream {
 // TF32-exact high part and a low part (hi = rn_tf32(x), lo = x - hi) and three m16n8k8 TF32 MMAs
 // (lo*hi + hi*lo + hi*hi, fp32 accumulate) replace one fp32 product -- "3xTF32", relative error ~2^-21.
 // W arrives in [KS][NT*CW + 8] slices (row pad 8 floats => conflict-free B-fragment loads); sA row strides are
-// 4 mod 32 floats => conflict-free A-fragment loads.  8 warps = 2 warp rows x 4 warp columns; a warp owns
-// MI = R/32 m16 tiles x NI = CW/32 n8 tiles of each of the NT column tiles.
+// 4 mod 32 floats => conflict-free A-fragment loads.  The warps form a WRn x WCn grid (2 x 4 for 8 warps); a warp owns
+// MI m16 tiles x NI n8 tiles of each of the NT column tiles.
 constexpr int kWPad = 8;
 
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
@@ -92,10 +92,13 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
 
 template <int R, int CW, int NT>
 struct Acc {
-    static constexpr int MI = R / 32;        // m16 tiles per warp (2 warp rows)
-    static constexpr int NI = CW / 32;       // n8 tiles per warp and column tile (4 warp columns)
-    static constexpr int RW = R / 2;         // rows per warp row
-    static constexpr int CWW = CW / 4;       // columns per warp column
+    static constexpr int WRn = (kWarps == 16 && R >= 64) ? 4 : 2;   // warp rows
+    static constexpr int WCn = kWarps / WRn;                         // warp columns
+    static constexpr int RW = R / WRn;       // rows per warp row
+    static constexpr int CWW = CW / WCn;     // columns per warp column
+    static constexpr int MI = RW / 16;       // m16 tiles per warp
+    static constexpr int NI = CWW / 8;       // n8 tiles per warp and column tile
+    static_assert(MI >= 1 && NI >= 1 && MI * 16 * WRn == R && NI * 8 * WCn == CW, "warp grid does not tile the block");
     float v[NT][MI][NI][4];
     __device__ __forceinline__ void zero() {
 #pragma unroll
@@ -116,7 +119,7 @@ __device__ __forceinline__ void gemm_acc(WStream& ws, const float* __restrict__ 
     constexpr int NCP = NC + kWPad;
     constexpr int KS = ((NC == 384) ? 8 : (NC == 192 ? 16 : (NC == 128 ? 16 : 32))) * (NC == 64 ? 1 : KM);   // rows per streamed slice
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wr = warp >> 2, wc = warp & 3;
+    const int wr = warp / A_::WCn, wc = warp % A_::WCn;
     const int g = lane >> 2, tig = lane & 3;
     const float* a_base = sA + (wr * A_::RW + g) * lda + tig;
     const int bcol = wc * A_::CWW + g;
@@ -179,7 +182,7 @@ template <int R, int CW, int NT, class F>
 __device__ __forceinline__ void tile_foreach(Acc<R, CW, NT>& acc, F f) {
     using A_ = Acc<R, CW, NT>;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wr = warp >> 2, wc = warp & 3;
+    const int wr = warp / A_::WCn, wc = warp % A_::WCn;
     const int g = lane >> 2, tig = lane & 3;
 #pragma unroll
     for (int t = 0; t < NT; ++t)
