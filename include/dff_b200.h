@@ -159,6 +159,11 @@ int64_t dff_debug_read_stash(dff_model_t* m, float* out_host, int64_t cap);
 int dff_debug_stash_layout(const dff_model_t* m, int* rows, int* samples, int* npad,
                            int64_t* layer_floats, int64_t offsets[11]);
 
+/* Test hook for the tcgen05 building block (csrc/dff_tc.cuh): D[64,N] = A[64,K] * B[N,K]^T with 3xTF32 split
+ * precision on the 5th-generation tensor cores (operands staged in shared memory, accumulator in TMEM), executed
+ * `reps` times by one CTA; *ms_out receives the CUDA-event time of the timed launch. Host pointers. */
+int dff_debug_tc_gemm(const float* a_host, const float* b_host, float* d_host, int n, int k, int reps, float* ms_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,6 +12,7 @@
 
 #include "../../include/dff_b200.h"
 #include "dff_kernel.cuh"
+#include "dff_tc.cuh"
 
 using namespace dff;
 
@@ -512,6 +513,31 @@ int64_t dff_debug_read_stash(dff_model_t* m, float* out_host, int64_t cap) {
     if (cudaMemcpy(out_host, m->d_scratch, n * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess)
         return fail(DFF_ECUDA, "stash copy failed");
     return n;
+}
+
+int dff_debug_tc_gemm(const float* a_host, const float* b_host, float* d_host, int n, int k, int reps, float* ms_out) {
+    if (!a_host || !b_host || !d_host) return fail(DFF_EINVAL, "NULL argument");
+    if (n < 8 || n > 256 || n % 8 || k < 8 || k % 8) return fail(DFF_EINVAL, "need 8 <= N <= 256 (multiple of 8) and K a multiple of 8");
+    const size_t smem = (size_t)(64 + n) * k * 2 * sizeof(float);
+    if (smem > 220 * 1024) return fail(DFF_EINVAL, "operands need %zu bytes of shared memory (> 220 KB)", smem);
+    float *dA = nullptr, *dB = nullptr, *dD = nullptr;
+    CUDA_TRY(cudaMalloc(&dA, 64 * (size_t)k * 4)); CUDA_TRY(cudaMalloc(&dB, (size_t)n * k * 4)); CUDA_TRY(cudaMalloc(&dD, 64 * (size_t)n * 4));
+    CUDA_TRY(cudaMemcpy(dA, a_host, 64 * (size_t)k * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(dB, b_host, (size_t)n * k * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaFuncSetAttribute(dff_tc_gemm_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+    dff_tc_gemm_test_kernel<<<1, 128, smem>>>(dA, dB, dD, n, k, 1);            // warm-up
+    CUDA_TRY(cudaEventRecord(e0));
+    dff_tc_gemm_test_kernel<<<1, 128, smem>>>(dA, dB, dD, n, k, reps < 1 ? 1 : reps);
+    CUDA_TRY(cudaEventRecord(e1));
+    CUDA_TRY(cudaDeviceSynchronize());
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms_out) *ms_out = ms;
+    CUDA_TRY(cudaMemcpy(d_host, dD, 64 * (size_t)n * 4, cudaMemcpyDeviceToHost));
+    cudaFree(dA); cudaFree(dB); cudaFree(dD); cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return DFF_OK;
 }
 
 int dff_debug_stash_layout(const dff_model_t* m, int* rows, int* samples, int* npad, int64_t* layer_floats, int64_t offsets[11]) {
