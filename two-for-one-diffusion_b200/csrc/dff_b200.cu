@@ -13,6 +13,7 @@
 #include "../../include/dff_b200.h"
 #include "dff_kernel.cuh"
 #include "dff_tc.cuh"
+#include "dff_kernel_tc.cuh"
 
 using namespace dff;
 
@@ -65,6 +66,10 @@ struct dff_model {
     uint32_t* d_flags = nullptr;
     float* d_sched = nullptr;  size_t d_sched_T = 0;
     int last_R = 0, last_S = 0;
+    // tcgen05 configuration (hidden = 64): job table + canonical hi/lo weight panels
+    bool tc_ok = false;
+    v2::TcJob* d_jobs = nullptr;
+    v2::TcArgs tc{};
 };
 
 namespace {
@@ -110,6 +115,21 @@ int launch_cfg(dff_model* m, const ModelDev& M, const StepArgs& A, int grid, cud
     return DFF_OK;
 }
 
+template <class C>
+int launch_tc(dff_model* m, const ModelDev& M, const StepArgs& A, int grid, cudaStream_t stream) {
+    static bool attr_set[8] = {false};
+    auto kern = v2::dff_fused_tc_kernel<C>;
+    const size_t smem = C::kSmemBytes;
+    if (!attr_set[m->device & 7]) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[m->device & 7] = true;
+    }
+    kern<<<grid, v2::kTcThreads, smem, stream>>>(M, A, m->tc);
+    CUDA_TRY(cudaGetLastError());
+    m->launches += 1;
+    return DFF_OK;
+}
+
 // Launch policy.  Three configurations of the same kernel:
 //   wide : R = 64 rows, 1 head per chunk, 4-stage ring, 1 CTA/SM   (anything; the only one for N > 32)
 //   tall : R = 32 rows, 2 heads per chunk, 4-stage ring, 1 CTA/SM  (small batches: fewer, fatter phases)
@@ -122,7 +142,7 @@ int launch(dff_model* m, StepArgs& A, cudaStream_t stream) {
     CUDA_TRY(cudaSetDevice(m->device));
     const int N = m->N;
     const int s64 = 64 / N, s32 = 32 / N;
-    enum { WIDE, TALL, DUO } cfg;
+    enum { WIDE, TALL, DUO, TC } cfg;
     const int need1 = (A.B + m->num_sms - 1) / m->num_sms;            // samples per CTA covering the batch with 1 CTA/SM
     const int need2 = (A.B + 2 * m->num_sms - 1) / (2 * m->num_sms);  // ... with 2 CTAs/SM
     // measured on B200 (profiles/r01/ablation.md): tall wins when the batch fits one wave at R = 32 (C2: 2244 vs 1658 duo
@@ -137,6 +157,21 @@ int launch(dff_model* m, StepArgs& A, cudaStream_t stream) {
         if (!strcmp(e, "wide")) cfg = WIDE;
         else if (!strcmp(e, "tall") && s32 >= 1) cfg = TALL;
         else if (!strcmp(e, "duo") && s32 >= 1 && kThreads == 256) cfg = DUO;
+        else if (!strcmp(e, "tc") && m->tc_ok) cfg = TC;
+    }
+    if (cfg == TC) {
+        // tcgen05 kernel: 64-row passes (MMA M = 64), 1 head per chunk, 1 CTA/SM
+        const int S = std::min(s64, std::max(need1, 1));
+        ModelDev M = m->md[1];
+        M.S = S;
+        const int n_groups = (A.B + S - 1) / S;
+        const int grid = std::min(n_groups, m->num_sms);
+        if (grid > m->scratch_ctas) return fail(DFF_EINVAL, "internal: grid %d exceeds scratch slots %d", grid, m->scratch_ctas);
+        const double slices = (double)((n_groups + grid - 1) / grid) * (double)A.n_steps * (double)m->tc.nslice_all;
+        if (slices >= 4.0e9) return fail(DFF_EINVAL, "n_steps %d too large for one launch; split the call (e.g. per save interval)", A.n_steps);
+        m->last_R = 64; m->last_S = S;
+        if (m->NP <= 12) return launch_tc<v2::TcCfg<12>>(m, M, A, grid, stream);
+        return launch_tc<v2::TcCfg<32>>(m, M, A, grid, stream);
     }
     int R, S, ctas;
     ModelDev M;
@@ -322,6 +357,93 @@ int dff_model_create(dff_model_t** out, int device, int num_beads, int hidden, i
         }
     }
 
+
+    // ---- tcgen05 configuration (hidden = 64): job table in issue order + canonical, pre-split weight panels.
+    // A panel is K/ks slices; a slice is [hi image | lo image], each the UMMA K-major no-swizzle layout of a
+    // [n rows x ks] tile: float offset ((k / 4) * n + row) * 4 + k % 4.  hi = rn_tf32(w), lo = w - hi.
+    struct TcJobHost { size_t offset; v2::TcJob j; };
+    std::vector<TcJobHost> tcj;
+    int tc_njobs_fwd = 0;
+    uint32_t tc_nslice_fwd = 0, tc_nslice_all = 0;
+    const bool tc_shape = (H == 64 && N <= 32);
+    if (tc_shape) {
+        auto job = [&](int K, int NN, auto&& fill /* (k, n) -> value */, int d_col, int a_slot, int acc_first, int wait_post,
+                       int dbuf, int commit_acc, int commit_d1) {
+            int KS = 8;
+            for (int cand = 8; cand <= K; cand += 8)
+                if (K % cand == 0 && 2 * cand * NN * 4 <= v2::kTcStageFloats * 4) KS = cand;
+            const size_t o = P.alloc((size_t)2 * K * NN);
+            for (int k = 0; k < K; ++k)
+                for (int n = 0; n < NN; ++n) {
+                    const float v = fill(k, n);
+                    uint32_t bits;
+                    memcpy(&bits, &v, 4);
+                    bits = (bits + 0x1000u) & 0xffffe000u;
+                    float hi;
+                    memcpy(&hi, &bits, 4);
+                    const int s = k / KS, kk = k % KS;
+                    const size_t at = o + (size_t)s * 2 * KS * NN + (size_t)((kk / 4) * NN + n) * 4 + (kk % 4);
+                    P.buf[at] = hi;
+                    P.buf[at + (size_t)KS * NN] = v - hi;
+                }
+            TcJobHost h{};
+            h.offset = o;
+            h.j.slice_bytes = (uint32_t)(2 * KS * NN * 4);
+            h.j.n_slices = (uint16_t)(K / KS); h.j.ks = (uint16_t)KS; h.j.n = (uint16_t)NN; h.j.d_col = (uint16_t)d_col;
+            h.j.a_slot = (uint8_t)a_slot; h.j.acc_first = (uint8_t)acc_first; h.j.wait_post = (uint8_t)wait_post;
+            h.j.dbuf = (uint8_t)dbuf; h.j.commit_acc = (uint8_t)commit_acc; h.j.commit_d1 = (uint8_t)commit_d1;
+            tcj.push_back(h);
+        };
+        const int cD = (int)v2::kColD, cA = (int)v2::kColAcc;
+        for (int l = 0; l < L; ++l) {
+            const float *Wq = LW(l, 2), *bq = LW(l, 3), *Wkv = LW(l, 4), *bkv = LW(l, 5), *Wo = LW(l, 8), *W1 = LW(l, 13), *W2 = LW(l, 15);
+            const size_t oA = lo[l].A;
+            auto qkv = [&](int hc, int wait_post) {
+                job(H + 8, 192, [&](int k, int n) -> float {
+                    const int t = n / 64, j = hc * 64 + n % 64;
+                    if (k < H) return t == 0 ? Wq[(size_t)j * H + k] : Wkv[(size_t)((t == 1 ? 0 : 512) + j) * H + k];
+                    if (k < H + 3) return t == 0 ? 0.f : P.buf[oA + (size_t)j * 4 + (k - H)];      // + A x_j  (k', v' only)
+                    if (k == H + 3) return t == 0 ? bq[j] : bkv[(t == 1 ? 0 : 512) + j];           // bias rides on the ones column
+                    return 0.f;
+                }, cD, 0, 0, wait_post, 1, 0, 0);
+            };
+            auto outp = [&](int hc, int commit_acc) {
+                job(64, 64, [&](int k, int d) -> float { return Wo[(size_t)d * 512 + hc * 64 + k]; }, cA, 1, hc > 0, 1, 0, commit_acc, 0);
+            };
+            qkv(0, 1); qkv(1, 0);
+            for (int hc = 0; hc < 8; ++hc) {
+                outp(hc, hc == 7);
+                if (hc + 2 < 8) qkv(hc + 2, 0);
+            }
+            job(H, 4 * H, [&](int k, int j) -> float { return W1[(size_t)j * H + k]; }, cD, 0, 0, 1, 0, 0, 1);
+            for (int c2 = 0; c2 < 4; ++c2)
+                job(64, 64, [&](int k, int d) -> float { return W2[(size_t)d * 4 * H + c2 * 64 + k]; }, cA, 1, c2 > 0, 1, 0, c2 == 3, 0);
+        }
+        tc_njobs_fwd = (int)tcj.size();
+        for (int l = L - 1; l >= 0; --l) {
+            const float *Wq = LW(l, 2), *Wkv = LW(l, 4), *Wo = LW(l, 8), *W1 = LW(l, 13), *W2 = LW(l, 15);
+            job(H, 4 * H, [&](int d, int j) -> float { return W2[(size_t)d * 4 * H + j]; }, cD, 0, 0, 1, 0, 0, 1);
+            for (int c2 = 0; c2 < 4; ++c2)
+                job(64, 64, [&](int j, int d) -> float { return W1[(size_t)(c2 * 64 + j) * H + d]; }, cA, 1, c2 > 0, 1, 0, c2 == 3, 0);
+            auto jdo = [&](int hc, int wait_post) {
+                job(H, 64, [&](int d, int j) -> float { return Wo[(size_t)d * 512 + hc * 64 + j]; }, cD, 0, 0, wait_post, 1, 0, 0);
+            };
+            jdo(0, 1); jdo(1, 0);
+            for (int hc = 0; hc < 8; ++hc) {
+                if (l > 0) {
+                    job(64, 64, [&](int j, int d) -> float { return Wq[(size_t)(hc * 64 + j) * H + d]; }, cA, 1, hc > 0, 1, 0, 0, 0);
+                    job(64, 64, [&](int j, int d) -> float { return Wkv[(size_t)(hc * 64 + j) * H + d]; }, cA, 1, 1, 1, 0, 0, 0);
+                    job(64, 64, [&](int j, int d) -> float { return Wkv[(size_t)(512 + hc * 64 + j) * H + d]; }, cA, 1, 1, 1, 0, hc == 7, 0);
+                }
+                if (hc + 2 < 8) jdo(hc + 2, 0);
+            }
+        }
+        for (int i = 0; i < (int)tcj.size(); ++i) {
+            if (i < tc_njobs_fwd) tc_nslice_fwd += tcj[i].j.n_slices;
+            tc_nslice_all += tcj[i].j.n_slices;
+        }
+    }
+
     auto cleanup = [&]() { dff_model_destroy(m); };
     if (cudaMalloc(&m->d_weights, P.buf.size() * sizeof(float)) != cudaSuccess) { cleanup(); return fail(DFF_ENOMEM, "cudaMalloc weights failed"); }
     if (cudaMemcpy(m->d_weights, P.buf.data(), P.buf.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) { cleanup(); return fail(DFF_ECUDA, "weight upload failed"); }
@@ -330,6 +452,17 @@ int dff_model_create(dff_model_t** out, int device, int num_beads, int hidden, i
         for (size_t i = 0; i < hs.size(); ++i) hs[i] = Seg{m->d_weights + segs[ci][i].offset, segs[ci][i].slice_bytes, segs[ci][i].n_slices};
         if (cudaMalloc(&m->d_segs[ci], hs.size() * sizeof(Seg)) != cudaSuccess) { cleanup(); return fail(DFF_ENOMEM, "cudaMalloc segs failed"); }
         if (cudaMemcpy(m->d_segs[ci], hs.data(), hs.size() * sizeof(Seg), cudaMemcpyHostToDevice) != cudaSuccess) { cleanup(); return fail(DFF_ECUDA, "segment upload failed"); }
+    }
+
+
+    if (tc_shape && (int)tcj.size() <= v2::kJobCap) {
+        std::vector<v2::TcJob> hj(tcj.size());
+        for (size_t i = 0; i < hj.size(); ++i) { hj[i] = tcj[i].j; hj[i].base = m->d_weights + tcj[i].offset; }
+        if (cudaMalloc(&m->d_jobs, hj.size() * sizeof(v2::TcJob)) != cudaSuccess) { cleanup(); return fail(DFF_ENOMEM, "cudaMalloc jobs failed"); }
+        if (cudaMemcpy(m->d_jobs, hj.data(), hj.size() * sizeof(v2::TcJob), cudaMemcpyHostToDevice) != cudaSuccess) { cleanup(); return fail(DFF_ECUDA, "job table upload failed"); }
+        m->tc.jobs = m->d_jobs; m->tc.njobs_fwd = tc_njobs_fwd; m->tc.njobs_all = (int)hj.size();
+        m->tc.nslice_fwd = tc_nslice_fwd; m->tc.nslice_all = tc_nslice_all;
+        m->tc_ok = true;
     }
 
     stash_geometry(32, m->NP, H, m->off[0], &m->layer_floats[0]);
@@ -371,6 +504,7 @@ void dff_model_destroy(dff_model_t* m) {
     if (m->d_scratch) cudaFree(m->d_scratch);
     if (m->d_flags) cudaFree(m->d_flags);
     if (m->d_sched) cudaFree(m->d_sched);
+    if (m->d_jobs) cudaFree(m->d_jobs);
     for (auto p : m->d_io) if (p) cudaFree(p);
     delete m;
 }

@@ -1,0 +1,872 @@
+// dff_kernel_tc.cuh -- tcgen05 / TMEM version of the fused score-network + integrator kernel (sm_100a).
+//
+// Same math, same stash, same integrator epilogues as dff_kernel.cuh (the mma.sync version); what changes is
+// how the dense projections run and how the CTA is organised:
+//
+//   * every projection is a chain of `tcgen05.mma.cta_group::1.kind::tf32` instructions (M = 64 rows, N = 64..256,
+//     K = 8 per instruction) issued by ONE thread; accumulators live in TMEM (448 of 512 columns), the epilogues
+//     read them back with `tcgen05.ld`;
+//   * fp32-grade accuracy = 3xTF32 split precision: activations are written by their producers directly in the
+//     UMMA canonical K-major layout as a TF32-exact high part and a low part, the weights are pre-split on the
+//     host; lo*hi + hi*lo + hi*hi accumulate in the fp32 TMEM accumulator;
+//   * weights arrive as pre-split, pre-laid-out [hi | lo] slices through a 3-stage ring filled by a dedicated
+//     TMA producer thread (cp.async.bulk + mbarrier expect_tx) and released by `tcgen05.commit`;
+//   * the CTA is warp-specialised: 8 compute warps (attention, softmax, LayerNorm, gates, GELU, integrators,
+//     TMEM epilogues) + 1 TMA producer warp + 1 MMA issuer warp.  The issuer follows a host-built job table, so
+//     the QKV projection of head chunk h+1 and the out-projection of chunk h-1 run on the tensor core WHILE the
+//     compute warps do the attention of chunk h (double-buffered TMEM accumulators);
+//   * the folded edge term  A x_j  and the q/k/v biases ride inside the QKV GEMM as 8 extra K rows
+//     (operand row = [n_hat | x0 x1 x2 1 0 0 0 0]), so that epilogue is a pure TMEM -> smem/stash copy.
+//
+// Shape support: hidden = 64 (chignolin-class nets), N <= PN beads.  Other shapes use dff_kernel.cuh.
+// Reference lines replaced: the same as dff_kernel.cuh (models/graph_transformer.py:87-111,143-159,178-329;
+// models/ddpm.py:195-251; dynamics/langevin.py:75-92; dynamics/langevin_cgnet.py:447-542,737-771).
+#pragma once
+#include "dff_kernel.cuh"
+#include <stdio.h>
+#include "dff_tc.cuh"
+
+namespace dff {
+namespace v2 {
+
+constexpr int kR = 64;                    // node rows per CTA pass = MMA M
+constexpr int kComputeThreads = 256;      // must equal dff::kThreads (the shared phase helpers stride by it)
+constexpr int kTcThreads = kComputeThreads + 64;   // + TMA producer warp + MMA issuer warp
+constexpr int kTcStages = 3;
+constexpr int kTcStageFloats = 4096;      // 16 KB: the largest slice, [hi|lo] x [8 k][256 n]
+constexpr int kCS = kR * 4 + 4;           // canonical chunk stride in floats (64 rows x 16 B + 16 B pad: bank spread)
+constexpr int kJobCap = 160;              // job-table entries cached in shared memory
+
+// TMEM column map (fp32 columns, 64 lanes used)
+constexpr uint32_t kColAcc = 0;           // [64]  att / ff / d m_hat / d n_hat accumulator
+constexpr uint32_t kColD = 64;            // [2 x 192] q|k'|v' double buffer, [256] FF hidden, [2 x 64] d o double buffer
+constexpr uint32_t kTmemCols = 512;
+
+// One GEMM of the per-step schedule, in issue order (built by the host, dff_b200.cu: build_tc_jobs).
+struct TcJob {
+    const float* base;        // weight panel: n_slices contiguous slices, each [hi image | lo image] of [ks/4][n][4] floats
+    uint32_t slice_bytes;
+    uint16_t n_slices, ks;
+    uint16_t n;               // MMA N (64, 192, 256)
+    uint16_t d_col;           // TMEM column of D (double-buffered jobs: column of buffer 0)
+    uint8_t a_slot;           // 0: A operand = the persistent buffer (n_hat / d ff / d att), 1: the rotating slot
+    uint8_t acc_first;        // 0: first MMA overwrites D, 1: accumulates
+    uint8_t wait_post;        // 1: wait for the next "operand ready" post of the compute warps before issuing
+    uint8_t dbuf;             // 1: D is double-buffered (QKV / d o jobs): gate on the drain counter, commit -> dq_ready[parity]
+    uint8_t commit_acc;       // 1: commit -> acc_ready after the job
+    uint8_t commit_d1;        // 1: commit -> d1_ready after the job
+    uint8_t pad_[2];
+};
+static_assert(sizeof(TcJob) == 32, "TcJob layout");
+
+struct TcArgs {
+    const TcJob* jobs;
+    int njobs_fwd, njobs_all;
+    uint32_t nslice_fwd, nslice_all;
+};
+
+// ------------------------------------------------------------------ configuration (hidden = 64)
+template <int PN_>
+struct TcCfg {
+    static constexpr int kHP = 64, kR = v2::kR, kHC = 1, kPN = PN_;
+    static constexpr int CWQ = 64, NCH = kHeads;
+    static constexpr int LDH = kHP + 4;
+    static constexpr int LDQ = 3 * CWQ + 4;
+    static constexpr int LDO = CWQ + 4;
+    static constexpr int EPL = kHP / 32;
+    static constexpr int NHAT_CHUNKS = kHP / 4 + 2;          // + [x0 x1 x2 1] chunk + zero chunk (K = 72 for the QKV jobs)
+    static constexpr int SLOT_CHUNKS = 16;
+    // shared memory carve-up (float offsets)
+    static constexpr int oN = 0;                             // [R][LDH] node stream / its gradient
+    static constexpr int oQKV = oN + kR * LDH;               // [R][LDQ] q|k'|v' of the head chunk; also the [R][LDH] row buffer
+    static constexpr int oO = oQKV + kR * LDQ;               // [R][LDO] d o of the head chunk (reverse pass)
+    static constexpr int oP = oO + kR * LDO;
+    static constexpr int oDS = oP + kR * kPN;
+    static constexpr int oNhatHi = oDS + kR * kPN;           // canonical persistent A operand
+    static constexpr int oNhatLo = oNhatHi + NHAT_CHUNKS * kCS;
+    static constexpr int oSlotHi = oNhatLo + NHAT_CHUNKS * kCS;   // canonical rotating A operand
+    static constexpr int oSlotLo = oSlotHi + SLOT_CHUNKS * kCS;
+    static constexpr int oW = oSlotLo + SLOT_CHUNKS * kCS;   // weight ring
+    static constexpr int oX = oW + kTcStages * kTcStageFloats;
+    static constexpr int oV = oX + kR * 4;
+    static constexpr int oDX = oV + kR * 4;
+    static constexpr int oTmp = oDX + kR * 4;
+    static constexpr int oJobs = oTmp + kR * 4;
+    static constexpr int oBar = oJobs + kJobCap * 8;
+    static constexpr int kFloats = oBar + 32;
+    static constexpr size_t kSmemBytes = (size_t)kFloats * sizeof(float);
+    static_assert(oNhatHi % 4 == 0 && oSlotHi % 4 == 0 && oW % 4 == 0 && oJobs % 4 == 0 && oBar % 4 == 0, "16-byte alignment");
+    static_assert(kSmemBytes <= 232448, "exceeds the 227 KB dynamic shared memory limit");
+};
+
+// barrier / counter block at oBar (uint64 slots)
+enum { B_FULL = 0, B_EMPTY = 3, B_DQ = 6, B_ACC = 8, B_D1 = 9, B_SLOT = 10, B_COUNT = 11 };
+
+// ------------------------------------------------------------------ small PTX helpers
+__device__ __forceinline__ void csync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 compute warps
+__device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+// Bounded waits: a protocol bug must fail loudly (trap -> CUDA error -> DFF_ECUDA), never hang the GPU.
+constexpr uint32_t kSpinLimit = 1u << 27;
+__device__ __noinline__ void watchdog_fail(int tag) {
+    printf("dff_fused_tc_kernel watchdog: wait %d never completed (block %d, thread %d)\n", tag, (int)blockIdx.x, (int)threadIdx.x);
+    __trap();
+}
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity, int tag) {
+    uint32_t n = 0;
+    while (!mbar_try(bar, parity))
+        if (++n > kSpinLimit) watchdog_fail(tag);
+}
+__device__ __forceinline__ void spin_until(const uint32_t* ctr, uint32_t target, int tag) {
+    uint32_t n = 0;
+    while (ld_acquire(ctr) < target)
+        if (++n > kSpinLimit) watchdog_fail(tag);
+}
+// TMEM -> registers: 16 consecutive fp32 columns of this thread's lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// D[64 x NCOLS] at TMEM column `col`: with M = 64 row m lives in lane (m % 16) + 32 * (m / 16), so compute warp w reads
+// lane quarter w & 3 (rows 16 (w & 3) .. + 15 in its lanes 0..15) and the column half w >> 2.
+// f(row, col_in_tile, v[16]) is called by the 16 lanes that own a row.
+template <int NCOLS, class F>
+__device__ __forceinline__ void tmem_foreach(uint32_t tmem_base, uint32_t col, F f) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = warp & 3, part = warp >> 2;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + col;
+    const int row = q * 16 + lane;
+#pragma unroll 1
+    for (int c = part * (NCOLS / 2); c < (part + 1) * (NCOLS / 2); c += 16) {
+        float v[16];
+        tmem_ld16(taddr + (uint32_t)c, v);
+        if (lane < 16) f(row, c, v);
+    }
+}
+
+// canonical (UMMA K-major, no swizzle) operand stores with the round-to-nearest TF32 hi/lo split
+__device__ __forceinline__ void can_store4(float* hi, float* lo, int r, int k4, const float4& x) {
+    float4 h, l;
+    tc::split4(x, h, l);
+    *reinterpret_cast<float4*>(hi + k4 * kCS + r * 4) = h;
+    *reinterpret_cast<float4*>(lo + k4 * kCS + r * 4) = l;
+}
+__device__ __forceinline__ void can_store2(float* hi, float* lo, int r, int col, float x0, float x1) {   // col even
+    float2 h, l;
+    h.x = __uint_as_float((__float_as_uint(x0) + 0x1000u) & 0xffffe000u); l.x = x0 - h.x;
+    h.y = __uint_as_float((__float_as_uint(x1) + 0x1000u) & 0xffffe000u); l.y = x1 - h.y;
+    const int o = (col >> 2) * kCS + r * 4 + (col & 3);
+    *reinterpret_cast<float2*>(hi + o) = h;
+    *reinterpret_cast<float2*>(lo + o) = l;
+}
+
+// ------------------------------------------------------------------ per-CTA context of the compute warps
+struct Ctx2 {
+    float *sN, *sNh, *sQKV, *sO, *sP, *sDS, *sX, *sV, *sDX, *sTmp;
+    float *nhat_hi, *nhat_lo, *slot_hi, *slot_lo;
+    uint64_t* bars;
+    uint32_t* posted;      // compute -> issuer: number of operands made ready
+    uint32_t* drained;     // compute -> issuer: number of double-buffered accumulators read back
+    uint32_t tmem;
+    uint32_t n_post, n_drain, n_acc, n_d1, n_slot;   // identical in every compute thread
+    bool slot_held;
+    float* stash;
+    int rows_act, S_act;
+
+    // operand written (generic proxy) -> visible to the tensor core (async proxy) -> tell the issuer
+    __device__ __forceinline__ void post() {
+        fence_proxy_async();
+        tc::fence_before_sync();
+        csync();
+        ++n_post;
+        if (threadIdx.x == 0) st_release(posted, n_post);
+    }
+    // wait for the double-buffered accumulator of the next QKV / d o job; returns its buffer index
+    __device__ __forceinline__ int dq_wait() {
+        const int b = n_drain & 1;
+        mbar_wait_wd(bars + B_DQ + b, (n_drain >> 1) & 1u, 1);
+        tc::fence_after_sync();
+        return b;
+    }
+    __device__ __forceinline__ void dq_release() {      // accumulator read back (and its smem copy written)
+        tc::fence_before_sync();
+        csync();
+        ++n_drain;
+        if (threadIdx.x == 0) st_release(drained, n_drain);
+    }
+    __device__ __forceinline__ void acc_wait() { mbar_wait_wd(bars + B_ACC, n_acc & 1u, 2); ++n_acc; tc::fence_after_sync(); }
+    __device__ __forceinline__ void d1_wait() { mbar_wait_wd(bars + B_D1, n_d1 & 1u, 3); ++n_d1; tc::fence_after_sync(); }
+    // the rotating slot may be overwritten once the MMAs of its previous use have completed
+    __device__ __forceinline__ void slot_acquire() {
+        if (!slot_held) {
+            if (n_slot > 0) mbar_wait_wd(bars + B_SLOT, (n_slot - 1) & 1u, 4);
+            slot_held = true;
+        }
+    }
+    __device__ __forceinline__ void slot_post() { slot_acquire(); slot_held = false; ++n_slot; post(); }
+};
+
+// ------------------------------------------------------------------ warp-per-row phases writing canonical operands
+// LayerNorm of sN rows -> canonical n_hat; stats -> stash; stashes the input rows.
+template <class C>
+__device__ __forceinline__ void ln_forward_rows_can(const float* sN, float* hi, float* lo, const float* __restrict__ gam,
+                                                    const float* __restrict__ bet, int H, float* st_rows, float* st_stats) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int r = warp; r < C::kR; r += kWarps) {
+        const int col = lane * 2;
+        const float2 x = *reinterpret_cast<const float2*>(sN + r * C::LDH + col);
+        const float mean = warp_sum(x.x + x.y) / (float)H;
+        const float d0 = x.x - mean, d1 = x.y - mean;
+        const float rstd = 1.0f / sqrtf(warp_sum(d0 * d0 + d1 * d1) / (float)H + kLnEps);
+        const float2 g = __ldg(reinterpret_cast<const float2*>(gam + col)), b = __ldg(reinterpret_cast<const float2*>(bet + col));
+        can_store2(hi, lo, r, col, d0 * rstd * g.x + b.x, d1 * rstd * g.y + b.y);
+        *reinterpret_cast<float2*>(st_rows + (size_t)r * H + col) = x;
+        if (lane == 0) { st_stats[r * 2] = mean; st_stats[r * 2 + 1] = rstd; }
+    }
+}
+
+// GatedResidual forward (graph_transformer.py:202-205): a = sA rows, n = sN -> out -> sN; then (if gam)
+// LayerNorm(out) -> canonical operand.  Stashes a, gate, out (and LN stats).
+template <class C>
+__device__ __forceinline__ void gate_ln_forward_rows_can(float* sN, const float* sA, float* hi, float* lo,
+                                                         const float* __restrict__ ga, const float* __restrict__ gb, int H,
+                                                         float* st_a, float* st_g, float* st_out,
+                                                         const float* __restrict__ gam, const float* __restrict__ bet,
+                                                         float* st_stats) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int r = warp; r < C::kR; r += kWarps) {
+        const int col = lane * 2;
+        const float2 a = *reinterpret_cast<const float2*>(sA + r * C::LDH + col);
+        const float2 n = *reinterpret_cast<const float2*>(sN + r * C::LDH + col);
+        const float2 wa = __ldg(reinterpret_cast<const float2*>(ga + col)), wb = __ldg(reinterpret_cast<const float2*>(gb + col));
+        const float z = warp_sum(a.x * wa.x + n.x * wb.x + a.y * wa.y + n.y * wb.y);
+        const float g = 1.0f / (1.0f + expf(-z));
+        const float2 o = make_float2(a.x * g + n.x * (1.0f - g), a.y * g + n.y * (1.0f - g));
+        *reinterpret_cast<float2*>(st_a + (size_t)r * H + col) = a;
+        *reinterpret_cast<float2*>(st_out + (size_t)r * H + col) = o;
+        *reinterpret_cast<float2*>(sN + r * C::LDH + col) = o;
+        if (lane == 0) st_g[r] = g;
+        if (gam == nullptr) continue;
+        const float mean = warp_sum(o.x + o.y) / (float)H;
+        const float d0 = o.x - mean, d1 = o.y - mean;
+        const float rstd = 1.0f / sqrtf(warp_sum(d0 * d0 + d1 * d1) / (float)H + kLnEps);
+        const float2 gg = __ldg(reinterpret_cast<const float2*>(gam + col)), bb = __ldg(reinterpret_cast<const float2*>(bet + col));
+        can_store2(hi, lo, r, col, d0 * rstd * gg.x + bb.x, d1 * rstd * gg.y + bb.y);
+        if (lane == 0) { st_stats[r * 2] = mean; st_stats[r * 2 + 1] = rstd; }
+    }
+}
+
+// Reverse of [LayerNorm ->] GatedResidual on rows.
+//   dout = sN (+ LN-backward of sD rows through (st_ln_in, stats, gam) when gam != nullptr)
+//   d(gate input a) -> canonical operand,  d(residual n) -> sN.      a, n, g come from the stash.
+template <class C>
+__device__ __forceinline__ void gate_backward_rows_can(float* sN, const float* sD, float* hi, float* lo, int H,
+                                                       const float* __restrict__ gam, const float* st_ln_in,
+                                                       const float* st_stats, const float* st_a, const float* st_n,
+                                                       const float* st_g, const float* __restrict__ ga,
+                                                       const float* __restrict__ gb) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int r = warp; r < C::kR; r += kWarps) {
+        const int col = lane * 2;
+        const float2 a = *reinterpret_cast<const float2*>(st_a + (size_t)r * H + col);
+        const float2 n = *reinterpret_cast<const float2*>(st_n + (size_t)r * H + col);
+        float2 d = *reinterpret_cast<const float2*>(sN + r * C::LDH + col);
+        const float g = st_g[r];
+        if (gam != nullptr) {
+            const float mean = st_stats[r * 2], rstd = st_stats[r * 2 + 1];
+            const float2 xin = *reinterpret_cast<const float2*>(st_ln_in + (size_t)r * H + col);
+            const float2 dd = *reinterpret_cast<const float2*>(sD + r * C::LDH + col);
+            const float2 gg = __ldg(reinterpret_cast<const float2*>(gam + col));
+            const float y0 = (xin.x - mean) * rstd, y1 = (xin.y - mean) * rstd;
+            const float dy0 = dd.x * gg.x, dy1 = dd.y * gg.y;
+            const float s1 = warp_sum(dy0 + dy1) / (float)H;
+            const float s2 = warp_sum(dy0 * y0 + dy1 * y1) / (float)H;
+            d.x += rstd * (dy0 - s1 - y0 * s2);
+            d.y += rstd * (dy1 - s1 - y1 * s2);
+        }
+        const float dg = warp_sum(d.x * (a.x - n.x) + d.y * (a.y - n.y));
+        const float dz = dg * g * (1.0f - g);
+        const float2 wa = __ldg(reinterpret_cast<const float2*>(ga + col)), wb = __ldg(reinterpret_cast<const float2*>(gb + col));
+        can_store2(hi, lo, r, col, d.x * g + dz * wa.x, d.y * g + dz * wa.y);
+        *reinterpret_cast<float2*>(sN + r * C::LDH + col) = make_float2(d.x * (1.0f - g) + dz * wb.x, d.y * (1.0f - g) + dz * wb.y);
+    }
+}
+
+// ------------------------------------------------------------------ forward pass (compute warps)
+template <class C>
+__device__ void forward_pass_tc(const ModelDev& M, Ctx2& c, float t_norm) {
+    constexpr int R = C::kR;
+    const int tid = threadIdx.x;
+    const int N = M.N, NP = M.NP, H = M.H;
+
+    // layer-0 node stream: W_n [onehot_i, t] + b_n   (graph_transformer.py:99-103)
+    for (int idx = tid; idx < R * C::kHP; idx += kThreads) {
+        const int r = idx / C::kHP, d = idx - r * C::kHP;
+        float v = 0.f;
+        if (r < c.rows_act) v = __ldg(M.emb + (r % N) * H + d) + t_norm * __ldg(M.embt + d);
+        c.sN[r * C::LDH + d] = v;
+    }
+    // augmented operand columns of this step: [x0 x1 x2 1] (chunk H/4); chunk H/4 + 1 stays zero
+    if (tid < R) {
+        const float4 xv = (tid < c.rows_act) ? make_float4(c.sX[tid * 4], c.sX[tid * 4 + 1], c.sX[tid * 4 + 2], 1.0f)
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+        can_store4(c.nhat_hi, c.nhat_lo, tid, C::kHP / 4, xv);
+    }
+    csync();
+    ln_forward_rows_can<C>(c.sN, c.nhat_hi, c.nhat_lo, M.layer[0].ln1_g, M.layer[0].ln1_b, H, c.stash + M.off[ST_NIN],
+                           c.stash + M.off[ST_STAT1]);
+    c.post();
+
+    for (int l = 0; l < M.L; ++l) {
+        const LayerDev& W = M.layer[l];
+        float* st = c.stash + (size_t)l * M.layer_floats;
+
+        for (int hc = 0; hc < C::NCH; ++hc) {
+            {   // q | k' | v' of the head chunk: TMEM -> shared (row-major, for the attention) + stash
+                const int b = c.dq_wait();
+                float* st_qkv = st + M.off[ST_QKV] + (size_t)hc * R * 3 * C::CWQ;
+                tmem_foreach<192>(c.tmem, kColD + b * 192, [&](int row, int col, const float (&v)[16]) {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) {
+                        const float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        *reinterpret_cast<float4*>(c.sQKV + row * C::LDQ + col + i) = o;
+                        *reinterpret_cast<float4*>(st_qkv + (size_t)row * (3 * C::CWQ) + col + i) = o;
+                    }
+                });
+                c.dq_release();
+            }
+            attn_nt(c.sQKV, C::LDQ, c.sQKV + C::CWQ, C::LDQ, c.sP, R * NP, NP, N, c.S_act, 1, kAttnScale);
+            csync();
+            softmax_rows<R, 1>(c.sP, NP, N, c.rows_act);
+            csync();
+            {
+                float* dst = st + M.off[ST_P] + (size_t)hc * R * NP;
+                for (int idx = tid; idx < (R * NP) / 4; idx += kThreads)
+                    reinterpret_cast<float4*>(dst)[idx] = reinterpret_cast<const float4*>(c.sP)[idx];
+            }
+            // o_i = sum_j p_ij v'_j - A x_i + c  -> canonical operand of the out-projection
+            attn_pv<false>(c.sP, R * NP, NP, c.sQKV + 2 * C::CWQ, C::LDQ, N, c.S_act, 1,
+                           [&](int, int s, int i, int d, const float4& a) {
+                const int row = s * N + i;
+                const float x0 = c.sX[row * 4], x1 = c.sX[row * 4 + 1], x2 = c.sX[row * 4 + 2];
+                const float4 cc = __ldg(reinterpret_cast<const float4*>(W.cvec + hc * C::CWQ + d));
+                float o[4] = {a.x + cc.x, a.y + cc.y, a.z + cc.z, a.w + cc.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float4 a4 = __ldg(reinterpret_cast<const float4*>(W.A + (hc * C::CWQ + d + e) * 4));
+                    o[e] -= a4.x * x0 + a4.y * x1 + a4.z * x2;
+                }
+                c.slot_acquire();
+                can_store4(c.slot_hi, c.slot_lo, row, d >> 2, make_float4(o[0], o[1], o[2], o[3]));
+            });
+            c.slot_post();
+        }
+        // attention block output -> row buffer; gated residual 1 + LayerNorm 2 -> canonical operand of FF1
+        c.acc_wait();
+        tmem_foreach<64>(c.tmem, kColAcc, [&](int row, int col, const float (&v)[16]) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(W.bo + col + i));
+                *reinterpret_cast<float4*>(c.sNh + row * C::LDH + col + i) = make_float4(v[i] + b.x, v[i + 1] + b.y, v[i + 2] + b.z, v[i + 3] + b.w);
+            }
+        });
+        tc::fence_before_sync();
+        csync();
+        gate_ln_forward_rows_can<C>(c.sN, c.sNh, c.nhat_hi, c.nhat_lo, W.g1a, W.g1b, H, st + M.off[ST_ATT], st + M.off[ST_G1],
+                                    st + M.off[ST_M], W.ln2_g, W.ln2_b, st + M.off[ST_STAT2]);
+        c.post();
+
+        // feed-forward: hidden pre-activations [R][4H] sit in TMEM; GELU 64 columns at a time -> slot -> FF2 accumulates
+        c.d1_wait();
+        {
+            const int warp = tid >> 5, lane = tid & 31;
+            const int q = warp & 3, part = warp >> 2, row = q * 16 + lane;
+            const uint32_t taddr = c.tmem + ((uint32_t)(q * 32) << 16) + kColD;
+            for (int ch = 0; ch < 4; ++ch) {
+                float v[2][16];
+                tmem_ld16(taddr + (uint32_t)(ch * 64 + part * 32), v[0]);
+                tmem_ld16(taddr + (uint32_t)(ch * 64 + part * 32 + 16), v[1]);
+                if (lane < 16) {
+#pragma unroll
+                    for (int u = 0; u < 2; ++u)
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4) {
+                            const int cl = part * 32 + u * 16 + i;          // column inside the 64-wide chunk
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(W.b1 + ch * 64 + cl));
+                            const float4 pre = make_float4(v[u][i] + b.x, v[u][i + 1] + b.y, v[u][i + 2] + b.z, v[u][i + 3] + b.w);
+                            *reinterpret_cast<float4*>(st + M.off[ST_H1] + (size_t)row * (4 * H) + ch * 64 + cl) = pre;
+                            c.slot_acquire();
+                            can_store4(c.slot_hi, c.slot_lo, row, cl >> 2, make_float4(gelu_f(pre.x), gelu_f(pre.y), gelu_f(pre.z), gelu_f(pre.w)));
+                        }
+                }
+                c.slot_post();
+            }
+        }
+        c.acc_wait();
+        tmem_foreach<64>(c.tmem, kColAcc, [&](int row, int col, const float (&v)[16]) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(W.b2 + col + i));
+                *reinterpret_cast<float4*>(c.sNh + row * C::LDH + col + i) = make_float4(v[i] + b.x, v[i + 1] + b.y, v[i + 2] + b.z, v[i + 3] + b.w);
+            }
+        });
+        tc::fence_before_sync();
+        csync();
+        // gated residual 2 (+ next layer's LayerNorm 1; its input rows are the next layer's n_in stash)
+        const bool last = (l + 1 == M.L);
+        float* stn = st + M.layer_floats;
+        gate_ln_forward_rows_can<C>(c.sN, c.sNh, c.nhat_hi, c.nhat_lo, W.g2a, W.g2b, H, st + M.off[ST_FF], st + M.off[ST_G2],
+                                    stn + M.off[ST_NIN], last ? nullptr : M.layer[l + 1].ln1_g,
+                                    last ? nullptr : M.layer[l + 1].ln1_b, last ? nullptr : stn + M.off[ST_STAT1]);
+        if (!last) c.post(); else csync();
+    }
+}
+
+// ------------------------------------------------------------------ reverse pass: sDX[r][0..2] = d sum(E) / d x_r
+template <class C>
+__device__ void backward_pass_tc(const ModelDev& M, Ctx2& c) {
+    constexpr int R = C::kR;
+    const int tid = threadIdx.x;
+    const int N = M.N, NP = M.NP, H = M.H;
+
+    for (int idx = tid; idx < R * C::kHP; idx += kThreads) {
+        const int r = idx / C::kHP, d = idx - r * C::kHP;
+        c.sN[r * C::LDH + d] = __ldg(M.dec_w + d);               // dE_r/dn_r = w_dec  (node_decoder, :106)
+    }
+    for (int idx = tid; idx < R * 4; idx += kThreads) c.sDX[idx] = 0.f;
+    csync();
+
+    for (int l = M.L - 1; l >= 0; --l) {
+        const LayerDev& W = M.layer[l];
+        float* st = c.stash + (size_t)l * M.layer_floats;
+
+        // gated residual 2 backward: d ff -> canonical operand, d m (partial) -> sN
+        gate_backward_rows_can<C>(c.sN, nullptr, c.nhat_hi, c.nhat_lo, H, nullptr, nullptr, nullptr, st + M.off[ST_FF],
+                                  st + M.off[ST_M], st + M.off[ST_G2], W.g2a, W.g2b);
+        c.post();
+        // feed-forward backward: d act [R][4H] in TMEM; times GELU' 64 columns at a time -> slot -> d m_hat accumulates
+        {
+            const int warp = tid >> 5, lane = tid & 31;
+            const int q = warp & 3, part = warp >> 2, row = q * 16 + lane;
+            const uint32_t taddr = c.tmem + ((uint32_t)(q * 32) << 16) + kColD;
+            float4 pre[2][4];
+            auto fetch = [&](int ch) {       // stash loads of the chunk's pre-activations, issued ahead of their use
+                if (lane < 16) {
+#pragma unroll
+                    for (int u = 0; u < 2; ++u)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            pre[u][i] = *reinterpret_cast<const float4*>(st + M.off[ST_H1] + (size_t)row * (4 * H) + ch * 64 + part * 32 + u * 16 + i * 4);
+                }
+            };
+            fetch(0);
+            c.d1_wait();
+            for (int ch = 0; ch < 4; ++ch) {
+                float v[2][16];
+                tmem_ld16(taddr + (uint32_t)(ch * 64 + part * 32), v[0]);
+                tmem_ld16(taddr + (uint32_t)(ch * 64 + part * 32 + 16), v[1]);
+                if (lane < 16) {
+                    c.slot_acquire();
+#pragma unroll
+                    for (int u = 0; u < 2; ++u)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int cl = part * 32 + u * 16 + i * 4;
+                            const float4 p = pre[u][i];
+                            can_store4(c.slot_hi, c.slot_lo, row, cl >> 2,
+                                       make_float4(v[u][i * 4] * gelu_grad_f(p.x), v[u][i * 4 + 1] * gelu_grad_f(p.y),
+                                                   v[u][i * 4 + 2] * gelu_grad_f(p.z), v[u][i * 4 + 3] * gelu_grad_f(p.w)));
+                        }
+                }
+                if (ch + 1 < 4) fetch(ch + 1);
+                c.slot_post();
+            }
+        }
+        c.acc_wait();
+        tmem_foreach<64>(c.tmem, kColAcc, [&](int row, int col, const float (&v)[16]) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4)
+                *reinterpret_cast<float4*>(c.sNh + row * C::LDH + col + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        });
+        tc::fence_before_sync();
+        csync();
+        // LayerNorm 2 backward + gated residual 1 backward: d att -> canonical operand, d n_in (residual part) -> sN
+        gate_backward_rows_can<C>(c.sN, c.sNh, c.nhat_hi, c.nhat_lo, H, W.ln2_g, st + M.off[ST_M], st + M.off[ST_STAT2],
+                                  st + M.off[ST_ATT], st + M.off[ST_NIN], st + M.off[ST_G1], W.g1a, W.g1b);
+        c.post();
+
+        for (int hc = 0; hc < C::NCH; ++hc) {
+            // start reloading q | k' | v' and p of this chunk; the copies land while d o is read back
+            stash_load_async<R>(c.sQKV, C::LDQ, st + M.off[ST_QKV] + (size_t)hc * R * 3 * C::CWQ, 3 * C::CWQ);
+            {
+                const float* src = st + M.off[ST_P] + (size_t)hc * R * NP;
+                for (int idx = tid; idx < (R * NP) / 4; idx += kThreads) cp_async16(c.sP + idx * 4, src + idx * 4);
+            }
+            {   // d o_chunk = d att x Wo_b[l][hc]: TMEM -> shared
+                const int b = c.dq_wait();
+                tmem_foreach<64>(c.tmem, kColD + b * 64, [&](int row, int col, const float (&v)[16]) {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4)
+                        *reinterpret_cast<float4*>(c.sO + row * C::LDO + col + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                });
+                cp_async_wait_all();
+                c.dq_release();
+            }
+            // dp_ij = do_i . v'_j
+            attn_nt(c.sO, C::LDO, c.sQKV + 2 * C::CWQ, C::LDQ, c.sDS, R * NP, NP, N, c.S_act, 1, 1.0f);
+            csync();
+            softmax_backward_rows<R, 1>(c.sDS, c.sP, NP, N, c.rows_act);
+            csync();
+            if (l > 0) {   // dq_i = s sum_j ds_ij k'_j  -> slot (operand of the Wq^T job)
+                attn_pv<false>(c.sDS, R * NP, NP, c.sQKV + C::CWQ, C::LDQ, N, c.S_act, 1,
+                               [&](int, int s, int i, int d, const float4& a) {
+                    c.slot_acquire();
+                    can_store4(c.slot_hi, c.slot_lo, s * N + i, d >> 2,
+                               make_float4(kAttnScale * a.x, kAttnScale * a.y, kAttnScale * a.z, kAttnScale * a.w));
+                });
+                c.slot_post();
+            }
+            // dk'_j = s sum_i ds_ij q_i  -> k' columns (k' is dead after dq) and slot (operand of the Wk^T job)
+            attn_pv<true>(c.sDS, R * NP, NP, c.sQKV, C::LDQ, N, c.S_act, 1, [&](int, int s, int j, int d, const float4& a) {
+                const float4 o = make_float4(kAttnScale * a.x, kAttnScale * a.y, kAttnScale * a.z, kAttnScale * a.w);
+                *reinterpret_cast<float4*>(c.sQKV + (s * N + j) * C::LDQ + C::CWQ + d) = o;
+                if (l > 0) { c.slot_acquire(); can_store4(c.slot_hi, c.slot_lo, s * N + j, d >> 2, o); }
+            });
+            if (l > 0) c.slot_post(); else csync();
+            // dv'_j = sum_i p_ij do_i  -> q columns (q is dead after dk') and slot (operand of the Wv^T job)
+            attn_pv<true>(c.sP, R * NP, NP, c.sO, C::LDO, N, c.S_act, 1, [&](int, int s, int j, int d, const float4& a) {
+                *reinterpret_cast<float4*>(c.sQKV + (s * N + j) * C::LDQ + d) = a;
+                if (l > 0) { c.slot_acquire(); can_store4(c.slot_hi, c.slot_lo, s * N + j, d >> 2, a); }
+            });
+            if (l > 0) c.slot_post(); else csync();
+            // dx_r += A_h^T (dk'_r + dv'_r - do_r)   (fixed summation order: deterministic)
+            for (int idx = tid; idx < c.rows_act * 3; idx += kThreads) {
+                const int r = idx / 3, cc = idx - r * 3;
+                float s = 0.f;
+                const float* dk = c.sQKV + r * C::LDQ + C::CWQ;
+                const float* dv = c.sQKV + r * C::LDQ;
+                const float* dO = c.sO + r * C::LDO;
+                const float* Ah = W.A + (hc * C::CWQ) * 4 + cc;
+#pragma unroll 4
+                for (int d = 0; d < 64; d += 4) {
+                    const float4 a = *reinterpret_cast<const float4*>(dk + d);
+                    const float4 b = *reinterpret_cast<const float4*>(dv + d);
+                    const float4 o = *reinterpret_cast<const float4*>(dO + d);
+                    s = fmaf(__ldg(Ah + (d + 0) * 4), a.x + b.x - o.x, s);
+                    s = fmaf(__ldg(Ah + (d + 1) * 4), a.y + b.y - o.y, s);
+                    s = fmaf(__ldg(Ah + (d + 2) * 4), a.z + b.z - o.z, s);
+                    s = fmaf(__ldg(Ah + (d + 3) * 4), a.w + b.w - o.w, s);
+                }
+                c.sDX[r * 4 + cc] += s;
+            }
+            csync();
+        }
+        if (l > 0) {
+            c.acc_wait();
+            tmem_foreach<64>(c.tmem, kColAcc, [&](int row, int col, const float (&v)[16]) {
+#pragma unroll
+                for (int i = 0; i < 16; i += 4)
+                    *reinterpret_cast<float4*>(c.sNh + row * C::LDH + col + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            });
+            tc::fence_before_sync();
+            csync();
+            ln_backward_rows<C>(c.sN, c.sNh, H, W.ln1_g, st + M.off[ST_NIN], st + M.off[ST_STAT1]);
+            csync();
+        }
+    }
+}
+
+// ------------------------------------------------------------------ the kernel
+template <class C>
+__global__ void __launch_bounds__(kTcThreads, 1)
+dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ StepArgs A, const __grid_constant__ TcArgs T) {
+    constexpr int R = C::kR;
+    extern __shared__ __align__(128) float smem[];
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int N = M.N;
+
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::oBar);
+    uint32_t* ctr = reinterpret_cast<uint32_t*>(bars + B_COUNT);     // [0] posted, [1] drained, [2] tmem base
+    TcJob* jobs = reinterpret_cast<TcJob*>(smem + C::oJobs);
+    const int njobs = A.need_backward ? T.njobs_all : T.njobs_fwd;
+    const uint32_t nslices = A.need_backward ? T.nslice_all : T.nslice_fwd;
+
+    const int n_groups = (A.B + M.S - 1) / M.S;
+    int my_groups = 0;
+    for (int g = blockIdx.x; g < n_groups; g += gridDim.x) ++my_groups;
+    const uint32_t reps = (uint32_t)my_groups * (uint32_t)A.n_steps;
+
+    for (int idx = tid; idx < C::oW; idx += kTcThreads) smem[idx] = 0.f;             // activations, operands
+    for (int idx = C::oX + tid; idx < C::oJobs; idx += kTcThreads) smem[idx] = 0.f;
+    for (int idx = tid; idx < njobs * 8; idx += kTcThreads)
+        reinterpret_cast<uint32_t*>(jobs)[idx] = reinterpret_cast<const uint32_t*>(T.jobs)[idx];
+    if (tid == 0) {
+        for (int i = 0; i < kTcStages; ++i) { mbar_init(bars + B_FULL + i, 1); mbar_init(bars + B_EMPTY + i, 1); }
+        mbar_init(bars + B_DQ, 1); mbar_init(bars + B_DQ + 1, 1);
+        mbar_init(bars + B_ACC, 1); mbar_init(bars + B_D1, 1); mbar_init(bars + B_SLOT, 1);
+        ctr[0] = 0; ctr[1] = 0;
+        fence_barrier_init();
+    }
+    if (warp == 0) tc::tmem_alloc(ctr + 2, kTmemCols);
+    fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = ctr[2];
+
+    if (warp == kComputeThreads / 32) {
+        // ===================================================== TMA producer: streams the weight slices of every job
+        if ((tid & 31) == 0) {
+            uint32_t slice_i = 0;
+            for (uint32_t rep = 0; rep < reps; ++rep)
+                for (int j = 0; j < njobs; ++j) {
+                    const TcJob jb = jobs[j];
+                    const char* src = reinterpret_cast<const char*>(jb.base);
+                    for (uint32_t s = 0; s < jb.n_slices; ++s, ++slice_i) {
+                        const uint32_t stg = slice_i % kTcStages, use = slice_i / kTcStages;
+                        if (use > 0) mbar_wait_wd(bars + B_EMPTY + stg, (use - 1) & 1u, 5);
+                        mbar_expect_tx(bars + B_FULL + stg, jb.slice_bytes);
+                        bulk_g2s(smem + C::oW + stg * kTcStageFloats, src + (size_t)s * jb.slice_bytes, jb.slice_bytes, bars + B_FULL + stg);
+                    }
+                }
+            (void)nslices;
+        }
+    } else if (warp == kComputeThreads / 32 + 1) {
+        // ===================================================== MMA issuer: walks the job table, one thread
+        if ((tid & 31) == 0) {
+            uint32_t slice_i = 0, post_seq = 0, dq_idx = 0;
+            const float* nhat_hi = smem + C::oNhatHi; const float* nhat_lo = smem + C::oNhatLo;
+            const float* slot_hi = smem + C::oSlotHi; const float* slot_lo = smem + C::oSlotLo;
+            for (uint32_t rep = 0; rep < reps; ++rep)
+                for (int j = 0; j < njobs; ++j) {
+                    const TcJob jb = jobs[j];
+                    if (jb.wait_post) {
+                        ++post_seq;
+                        spin_until(ctr, post_seq, 7);
+                    }
+                    uint32_t dcol = jb.d_col;
+                    if (jb.dbuf) {
+                        if (dq_idx >= 2) spin_until(ctr + 1, dq_idx - 1, 8);
+                        dcol += (dq_idx & 1u) * jb.n;
+                    }
+                    tc::fence_after_sync();
+                    const float* ahi = jb.a_slot ? slot_hi : nhat_hi;
+                    const float* alo = jb.a_slot ? slot_lo : nhat_lo;
+                    const uint32_t idesc = tc::idesc_tf32(64, jb.n);
+                    const uint32_t d_tmem = tmem + dcol;
+                    const uint32_t blbo = (uint32_t)jb.n * 16u;
+                    uint32_t acc = jb.acc_first;
+                    for (uint32_t s = 0; s < jb.n_slices; ++s, ++slice_i) {
+                        const uint32_t stg = slice_i % kTcStages, use = slice_i / kTcStages;
+                        mbar_wait_wd(bars + B_FULL + stg, use & 1u, 6);
+                        tc::fence_after_sync();
+                        const float* bhi = smem + C::oW + stg * kTcStageFloats;
+                        const float* blo = bhi + (uint32_t)jb.ks * jb.n;
+                        for (uint32_t kk = 0; kk < jb.ks; kk += 8) {
+                            const uint32_t ca = (s * jb.ks + kk) >> 2, cb = kk >> 2;
+                            const uint64_t dah = tc::smem_desc(ahi + ca * kCS, kCS * 4, 128), dal = tc::smem_desc(alo + ca * kCS, kCS * 4, 128);
+                            const uint64_t dbh = tc::smem_desc(bhi + cb * jb.n * 4, blbo, 128), dbl = tc::smem_desc(blo + cb * jb.n * 4, blbo, 128);
+                            tc::mma_tf32_ss(d_tmem, dal, dbh, idesc, acc);
+                            tc::mma_tf32_ss(d_tmem, dah, dbl, idesc, 1u);
+                            tc::mma_tf32_ss(d_tmem, dah, dbh, idesc, 1u);
+                            acc = 1u;
+                        }
+                        tc::commit(bars + B_EMPTY + stg);
+                    }
+                    if (jb.a_slot) tc::commit(bars + B_SLOT);
+                    if (jb.dbuf) { tc::commit(bars + B_DQ + (dq_idx & 1u)); ++dq_idx; }
+                    if (jb.commit_acc) tc::commit(bars + B_ACC);
+                    if (jb.commit_d1) tc::commit(bars + B_D1);
+                }
+        }
+    } else {
+        // ===================================================== compute warps
+        Ctx2 c;
+        c.sN = smem + C::oN; c.sQKV = smem + C::oQKV; c.sNh = c.sQKV; c.sO = smem + C::oO;
+        c.sP = smem + C::oP; c.sDS = smem + C::oDS; c.sX = smem + C::oX; c.sV = smem + C::oV;
+        c.sDX = smem + C::oDX; c.sTmp = smem + C::oTmp;
+        c.nhat_hi = smem + C::oNhatHi; c.nhat_lo = smem + C::oNhatLo; c.slot_hi = smem + C::oSlotHi; c.slot_lo = smem + C::oSlotLo;
+        c.bars = bars; c.posted = ctr; c.drained = ctr + 1; c.tmem = tmem;
+        c.n_post = c.n_drain = c.n_acc = c.n_d1 = c.n_slot = 0; c.slot_held = false;
+        c.stash = M.scratch + (size_t)blockIdx.x * M.scratch_per_cta;
+
+        uint32_t flags = 0;
+        for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
+            const int s0 = g * M.S;
+            c.S_act = min(M.S, A.B - s0);
+            c.rows_act = c.S_act * N;
+            for (int idx = tid; idx < R * 3; idx += kThreads) {
+                const int r = idx / 3, cc = idx - r * 3;
+                const bool ok = r < c.rows_act;
+                c.sX[r * 4 + cc] = ok ? A.x[((size_t)s0 * N + r) * 3 + cc] : 0.f;
+                c.sV[r * 4 + cc] = (ok && A.v != nullptr) ? A.v[((size_t)s0 * N + r) * 3 + cc] : 0.f;
+            }
+            csync();
+
+            for (int step = 0; step < A.n_steps; ++step) {
+                // center_zero (utils.py:65-70); entry check of assert_center_zero (utils.py:73-86) as a flag
+                if (tid < c.S_act * 3) {
+                    const int s = tid / 3, cc = tid - s * 3;
+                    float m = 0.f;
+                    for (int i = 0; i < N; ++i) m += c.sX[(s * N + i) * 4 + cc];
+                    m = m / (float)N;
+                    if (A.mode == MODE_DDPM && fabsf(m) >= 1e-3f) flags |= 2u;
+                    for (int i = 0; i < N; ++i) c.sX[(s * N + i) * 4 + cc] -= m;
+                }
+                csync();
+                const int it = A.t_start - step;
+                const float t_norm = (A.mode == MODE_DDPM) ? (float)it / (float)A.T : A.t_norm;
+
+                forward_pass_tc<C>(M, c, t_norm);
+                if (A.energy_out != nullptr) {   // node_decoder (graph_transformer.py:106)
+                    const int lane = tid & 31;
+                    for (int r = warp; r < c.rows_act; r += kWarps) {
+                        float s = 0.f;
+                        for (int d = lane; d < M.H; d += 32) s += c.sN[r * C::LDH + d] * __ldg(M.dec_w + d);
+                        s = warp_sum(s);
+                        if (lane == 0) A.energy_out[(size_t)s0 * N + r] = s + M.dec_b;
+                    }
+                }
+                csync();
+                if (A.need_backward) backward_pass_tc<C>(M, c);
+                csync();
+
+                if (A.mode == MODE_SCORE) {
+                    if (A.eps_out != nullptr)
+                        for (int idx = tid; idx < c.rows_act * 3; idx += kThreads) {
+                            const int r = idx / 3, cc = idx - r * 3;
+                            A.eps_out[((size_t)s0 * N + r) * 3 + cc] = -c.sDX[r * 4 + cc];
+                        }
+                } else if (A.mode == MODE_DDPM) {
+                    // p_mean_variance + p_sample + loop tail (models/ddpm.py:195-232, 248-251); eps = -dE/dx
+                    if (tid < c.S_act * 3) {
+                        const int s = tid / 3, cc = tid - s * 3;
+                        const float cr = A.sched[0][it], crm1 = A.sched[1][it], c1 = A.sched[2][it], c2 = A.sched[3][it];
+                        const float sigma = (it == 0) ? 0.f : expf(0.5f * A.sched[4][it]);
+                        float me = 0.f;
+                        for (int i = 0; i < N; ++i) me += -c.sDX[(s * N + i) * 4 + cc];
+                        me = me / (float)N;
+                        float mx0 = 0.f;
+                        for (int i = 0; i < N; ++i) {
+                            const int o = (s * N + i) * 4 + cc;
+                            const float e = -c.sDX[o] - me;
+                            const float x0 = cr * c.sX[o] - crm1 * e;
+                            c.sTmp[o] = x0;
+                            mx0 += x0;
+                        }
+                        mx0 = mx0 / (float)N;
+                        float mz = 0.f;
+                        for (int i = 0; i < N; ++i) {
+                            const int o = (s * N + i) * 4 + cc;
+                            const size_t ge = ((size_t)(s0 + s) * N + i) * 3 + cc;
+                            const float z = (A.noise != nullptr)
+                                                ? A.noise[(size_t)step * A.B * N * 3 + ge]
+                                                : philox_normal(A.seed, A.offset + (unsigned long long)step, (uint32_t)ge);
+                            c.sDX[o] = z;
+                            mz += z;
+                        }
+                        mz = mz / (float)N;
+                        float mn = 0.f;
+                        for (int i = 0; i < N; ++i) {
+                            const int o = (s * N + i) * 4 + cc;
+                            const float mean = c1 * (c.sTmp[o] - mx0) + c2 * c.sX[o];
+                            float xn = mean + sigma * (c.sDX[o] - mz);
+                            if (!(fabsf(xn) <= 3.0e38f)) flags |= 4u;
+                            if (xn > 1000.f || xn < -1000.f) { flags |= 1u; xn = fminf(fmaxf(xn, -1000.f), 1000.f); }
+                            c.sX[o] = xn;
+                            mn += xn;
+                        }
+                        mn = mn / (float)N;
+                        for (int i = 0; i < N; ++i) c.sX[(s * N + i) * 4 + cc] -= mn;
+                    }
+                } else {
+                    // ForcesWrapper (dynamics/langevin.py:78-87) + _langevin_timestep / _overdamped_timestep
+                    for (int idx = tid; idx < c.rows_act * 3; idx += kThreads) {
+                        const int r = idx / 3, cc = idx - r * 3;
+                        const int o = r * 4 + cc;
+                        const size_t ge = ((size_t)s0 * N + r) * 3 + cc;
+                        const float z = (A.noise != nullptr)
+                                            ? A.noise[(size_t)step * A.B * N * 3 + ge]
+                                            : philox_normal(A.seed, A.offset + (unsigned long long)step, (uint32_t)ge);
+                        const float F = (-c.sDX[o]) * A.force_scale;
+                        float x = c.sX[o];
+                        if (A.mode == MODE_BAOAB) {
+                            const float m = __ldg(A.mass + (r % N));
+                            float v = c.sV[o];
+                            v = v + A.dt * F / m;                 // B
+                            x = x + v * A.dt / 2.0f;              // A
+                            const float eta = sqrtf(A.inv_beta / m) * z;
+                            v = v * A.vscale;                      // O
+                            v = v + A.noisescale * eta;
+                            x = x + v * A.dt / 2.0f;              // A
+                            c.sV[o] = v;
+                        } else {
+                            x = x + F * A.dtau + A.bd_sigma * z;       // bd_sigma = sqrt(2 dtau / beta)
+                        }
+                        if (!(fabsf(x) <= 3.0e38f)) flags |= 4u;
+                        c.sX[o] = x;
+                    }
+                    if (A.save_interval > 0 && (step + 1) % A.save_interval == 0) {
+                        csync();
+                        const int f = step / A.save_interval;
+                        if (A.frames != nullptr)
+                            for (int idx = tid; idx < c.rows_act * 3; idx += kThreads) {
+                                const int r = idx / 3, cc = idx - r * 3;
+                                A.frames[((size_t)f * A.B + s0) * N * 3 + (size_t)r * 3 + cc] = c.sX[r * 4 + cc];
+                            }
+                        if (A.ke != nullptr && A.mode == MODE_BAOAB && tid < c.S_act) {
+                            float ke = 0.f;
+                            for (int i = 0; i < N; ++i) {
+                                const float* v = c.sV + (tid * N + i) * 4;
+                                ke += __ldg(A.mass + i) * v[0] * v[0] + __ldg(A.mass + i) * v[1] * v[1] + __ldg(A.mass + i) * v[2] * v[2];
+                            }
+                            A.ke[(size_t)f * A.B + s0 + tid] = 0.5f * ke;
+                        }
+                    }
+                }
+                csync();
+            }
+            if (A.mode != MODE_SCORE) {
+                for (int idx = tid; idx < c.rows_act * 3; idx += kThreads) {
+                    const int r = idx / 3, cc = idx - r * 3;
+                    A.x[((size_t)s0 * N + r) * 3 + cc] = c.sX[r * 4 + cc];
+                    if (A.v != nullptr) A.v[((size_t)s0 * N + r) * 3 + cc] = c.sV[r * 4 + cc];
+                }
+            }
+            csync();
+        }
+        if (A.flags != nullptr && flags != 0) atomicOr(A.flags, flags);
+    }
+
+    // teardown: every MMA has completed (the compute warps waited on the last accumulator) before TMEM is freed
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_free(tmem, kTmemCols);
+}
+
+}  // namespace v2
+}  // namespace dff
