@@ -126,6 +126,23 @@ int launch_tc(dff_model* m, const ModelDev& M, const StepArgs& A, int grid, cuda
     }
     kern<<<grid, v2::kTcThreads, smem, stream>>>(M, A, m->tc);
     CUDA_TRY(cudaGetLastError());
+#ifdef DFF_TC_PROFILE
+    if (m->tc.dbg) {     // developer build: print the per-CTA wait-cycle breakdown of this launch (synchronises)
+        std::vector<long long> h((size_t)grid * 16 + 32);
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        CUDA_TRY(cudaMemcpy(h.data(), m->tc.dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        double s[16] = {0};
+        for (int b = 0; b < grid; ++b) for (int i = 0; i < 16; ++i) s[i] += (double)h[(size_t)b * 16 + i] / grid;
+        fprintf(stderr, "[tc profile] grid %d steps %d: compute total %.0f cyc; waits dq %.0f acc %.0f d1 %.0f slot %.0f | issuer total %.0f: post %.0f drain %.0f weights %.0f | producer empty-wait %.0f\n",
+                grid, A.n_steps, s[7], s[0], s[1], s[2], s[3], s[12], s[9], s[10], s[11], s[8]);
+        static const char* names[23] = {"f.init+ln", "dq_wait", "f.qkv_epi", "f.attn", "f.slot_post", "acc_wait", "f.acc_epi", "f.gate+post", "d1_wait", "f.d1copy",
+                                        "f.gelu", "b.gate2+post", "b.d1copy", "b.gelu'", "b.accepi+gate1+post", "b.reload_issue", "b.do_epi", "b.ds", "b.dq+post",
+                                        "b.dk+post", "b.dv+post", "b.acc+lnbwd", "integrator"};
+        fprintf(stderr, "[tc phases, CTA 0, cycles per step]");
+        for (int i = 0; i < 23; ++i) fprintf(stderr, " %s %.0f |", names[i], (double)h[(size_t)grid * 16 + i] / A.n_steps);
+        fprintf(stderr, "\n");
+    }
+#endif
     m->launches += 1;
     return DFF_OK;
 }
@@ -463,6 +480,10 @@ int dff_model_create(dff_model_t** out, int device, int num_beads, int hidden, i
         m->tc.jobs = m->d_jobs; m->tc.njobs_fwd = tc_njobs_fwd; m->tc.njobs_all = (int)hj.size();
         m->tc.nslice_fwd = tc_nslice_fwd; m->tc.nslice_all = tc_nslice_all;
         m->tc_ok = true;
+#ifdef DFF_TC_PROFILE
+        if (cudaMalloc(&m->tc.dbg, ((size_t)m->num_sms * 16 + 32) * sizeof(long long)) != cudaSuccess) m->tc.dbg = nullptr;
+        else cudaMemset(m->tc.dbg, 0, ((size_t)m->num_sms * 16 + 32) * sizeof(long long));
+#endif
     }
 
     stash_geometry(32, m->NP, H, m->off[0], &m->layer_floats[0]);

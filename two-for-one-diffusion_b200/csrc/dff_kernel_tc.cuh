@@ -63,6 +63,7 @@ struct TcArgs {
     const TcJob* jobs;
     int njobs_fwd, njobs_all;
     uint32_t nslice_fwd, nslice_all;
+    long long* dbg;           // [grid][16] wait-cycle counters (DFF_TC_PROFILE builds), else NULL
 };
 
 // ------------------------------------------------------------------ configuration (hidden = 64)
@@ -138,6 +139,14 @@ __device__ __forceinline__ void spin_until(const uint32_t* ctr, uint32_t target,
     while (ld_acquire(ctr) < target)
         if (++n > kSpinLimit) watchdog_fail(tag);
 }
+// Optional wait-time accounting (-DDFF_TC_PROFILE): cycles spent in each kind of wait, per CTA, written to T.dbg.
+#ifdef DFF_TC_PROFILE
+#define TCP_BEGIN() const long long tcp_t0_ = clock64()
+#define TCP_END(arr, k) (arr)[k] += clock64() - tcp_t0_
+#else
+#define TCP_BEGIN() do { } while (0)
+#define TCP_END(arr, k) do { } while (0)
+#endif
 // TMEM -> registers: 16 consecutive fp32 columns of this thread's lane
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     uint32_t r[16];
@@ -152,18 +161,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 }
 // D[64 x NCOLS] at TMEM column `col`: with M = 64 row m lives in lane (m % 16) + 32 * (m / 16), so compute warp w reads
 // lane quarter w & 3 (rows 16 (w & 3) .. + 15 in its lanes 0..15) and the column half w >> 2.
-// f(row, col_in_tile, v[16]) is called by the 16 lanes that own a row.
+// f(row, col_in_tile, v[16]) is called by the lanes that own an active row (row < rows).
 template <int NCOLS, class F>
-__device__ __forceinline__ void tmem_foreach(uint32_t tmem_base, uint32_t col, F f) {
+__device__ __forceinline__ void tmem_foreach(uint32_t tmem_base, uint32_t col, int rows, F f) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = warp & 3, part = warp >> 2;
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + col;
     const int row = q * 16 + lane;
+    if (q * 16 >= rows) return;                    // warp-uniform: this lane quarter holds no active row
 #pragma unroll 1
     for (int c = part * (NCOLS / 2); c < (part + 1) * (NCOLS / 2); c += 16) {
         float v[16];
         tmem_ld16(taddr + (uint32_t)c, v);
-        if (lane < 16) f(row, c, v);
+        if (lane < 16 && row < rows) f(row, c, v);
     }
 }
 
@@ -193,6 +203,13 @@ struct Ctx2 {
     uint32_t tmem;
     uint32_t n_post, n_drain, n_acc, n_d1, n_slot;   // identical in every compute thread
     bool slot_held;
+    long long tw[8];       // DFF_TC_PROFILE: cycles waited on {dq, acc, d1, slot}
+#ifdef DFF_TC_PROFILE
+    long long ph[32], last;
+    __device__ __forceinline__ void mark(int k) { const long long t = clock64(); ph[k] += t - last; last = t; }
+#else
+    __device__ __forceinline__ void mark(int) {}
+#endif
     float* stash;
     int rows_act, S_act;
 
@@ -207,7 +224,9 @@ struct Ctx2 {
     // wait for the double-buffered accumulator of the next QKV / d o job; returns its buffer index
     __device__ __forceinline__ int dq_wait() {
         const int b = n_drain & 1;
+        TCP_BEGIN();
         mbar_wait_wd(bars + B_DQ + b, (n_drain >> 1) & 1u, 1);
+        TCP_END(tw, 0);
         tc::fence_after_sync();
         return b;
     }
@@ -217,12 +236,14 @@ struct Ctx2 {
         ++n_drain;
         if (threadIdx.x == 0) st_release(drained, n_drain);
     }
-    __device__ __forceinline__ void acc_wait() { mbar_wait_wd(bars + B_ACC, n_acc & 1u, 2); ++n_acc; tc::fence_after_sync(); }
-    __device__ __forceinline__ void d1_wait() { mbar_wait_wd(bars + B_D1, n_d1 & 1u, 3); ++n_d1; tc::fence_after_sync(); }
+    __device__ __forceinline__ void acc_wait() { TCP_BEGIN(); mbar_wait_wd(bars + B_ACC, n_acc & 1u, 2); TCP_END(tw, 1); ++n_acc; tc::fence_after_sync(); }
+    __device__ __forceinline__ void d1_wait() { TCP_BEGIN(); mbar_wait_wd(bars + B_D1, n_d1 & 1u, 3); TCP_END(tw, 2); ++n_d1; tc::fence_after_sync(); }
     // the rotating slot may be overwritten once the MMAs of its previous use have completed
     __device__ __forceinline__ void slot_acquire() {
         if (!slot_held) {
+            TCP_BEGIN();
             if (n_slot > 0) mbar_wait_wd(bars + B_SLOT, (n_slot - 1) & 1u, 4);
+            TCP_END(tw, 3);
             slot_held = true;
         }
     }
@@ -230,12 +251,13 @@ struct Ctx2 {
 };
 
 // ------------------------------------------------------------------ warp-per-row phases writing canonical operands
+// (only the active rows are processed; pad rows of the operands hold stale finite values whose products are never read)
 // LayerNorm of sN rows -> canonical n_hat; stats -> stash; stashes the input rows.
 template <class C>
 __device__ __forceinline__ void ln_forward_rows_can(const float* sN, float* hi, float* lo, const float* __restrict__ gam,
-                                                    const float* __restrict__ bet, int H, float* st_rows, float* st_stats) {
+                                                    const float* __restrict__ bet, int H, int rows, float* st_rows, float* st_stats) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int r = warp; r < C::kR; r += kWarps) {
+    for (int r = warp; r < rows; r += kWarps) {
         const int col = lane * 2;
         const float2 x = *reinterpret_cast<const float2*>(sN + r * C::LDH + col);
         const float mean = warp_sum(x.x + x.y) / (float)H;
@@ -252,12 +274,12 @@ __device__ __forceinline__ void ln_forward_rows_can(const float* sN, float* hi, 
 // LayerNorm(out) -> canonical operand.  Stashes a, gate, out (and LN stats).
 template <class C>
 __device__ __forceinline__ void gate_ln_forward_rows_can(float* sN, const float* sA, float* hi, float* lo,
-                                                         const float* __restrict__ ga, const float* __restrict__ gb, int H,
+                                                         const float* __restrict__ ga, const float* __restrict__ gb, int H, int rows,
                                                          float* st_a, float* st_g, float* st_out,
                                                          const float* __restrict__ gam, const float* __restrict__ bet,
                                                          float* st_stats) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int r = warp; r < C::kR; r += kWarps) {
+    for (int r = warp; r < rows; r += kWarps) {
         const int col = lane * 2;
         const float2 a = *reinterpret_cast<const float2*>(sA + r * C::LDH + col);
         const float2 n = *reinterpret_cast<const float2*>(sN + r * C::LDH + col);
@@ -283,13 +305,13 @@ __device__ __forceinline__ void gate_ln_forward_rows_can(float* sN, const float*
 //   dout = sN (+ LN-backward of sD rows through (st_ln_in, stats, gam) when gam != nullptr)
 //   d(gate input a) -> canonical operand,  d(residual n) -> sN.      a, n, g come from the stash.
 template <class C>
-__device__ __forceinline__ void gate_backward_rows_can(float* sN, const float* sD, float* hi, float* lo, int H,
+__device__ __forceinline__ void gate_backward_rows_can(float* sN, const float* sD, float* hi, float* lo, int H, int rows,
                                                        const float* __restrict__ gam, const float* st_ln_in,
                                                        const float* st_stats, const float* st_a, const float* st_n,
                                                        const float* st_g, const float* __restrict__ ga,
                                                        const float* __restrict__ gb) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int r = warp; r < C::kR; r += kWarps) {
+    for (int r = warp; r < rows; r += kWarps) {
         const int col = lane * 2;
         const float2 a = *reinterpret_cast<const float2*>(st_a + (size_t)r * H + col);
         const float2 n = *reinterpret_cast<const float2*>(st_n + (size_t)r * H + col);
@@ -315,30 +337,267 @@ __device__ __forceinline__ void gate_backward_rows_can(float* sN, const float* s
     }
 }
 
+// sN += LayerNorm-backward(sD) through (st_ln_in, stats, gam)
+template <class C>
+__device__ __forceinline__ void ln_backward_rows_tc(float* sN, const float* sD, int H, int rows, const float* __restrict__ gam,
+                                                    const float* st_ln_in, const float* st_stats) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int r = warp; r < rows; r += kWarps) {
+        const int col = lane * 2;
+        const float mean = st_stats[r * 2], rstd = st_stats[r * 2 + 1];
+        const float2 xin = *reinterpret_cast<const float2*>(st_ln_in + (size_t)r * H + col);
+        const float2 dd = *reinterpret_cast<const float2*>(sD + r * C::LDH + col);
+        const float2 gg = __ldg(reinterpret_cast<const float2*>(gam + col));
+        const float y0 = (xin.x - mean) * rstd, y1 = (xin.y - mean) * rstd;
+        const float dy0 = dd.x * gg.x, dy1 = dd.y * gg.y;
+        const float s1 = warp_sum(dy0 + dy1) / (float)H;
+        const float s2 = warp_sum(dy0 * y0 + dy1 * y1) / (float)H;
+        float2 d = *reinterpret_cast<const float2*>(sN + r * C::LDH + col);
+        d.x += rstd * (dy0 - s1 - y0 * s2);
+        d.y += rstd * (dy1 - s1 - y1 * s2);
+        *reinterpret_cast<float2*>(sN + r * C::LDH + col) = d;
+    }
+}
+
+// ------------------------------------------------------------------ row-local attention (a group of LPR lanes owns one node row)
+// LPR = 16 lanes per row for N <= 16 beads (two rows per warp), 32 for N <= 32.  Inside a group the lane index is the key
+// index j while logits / probabilities are formed and the output-column group (DPL = 64 / LPR columns) while values are
+// accumulated, so logits -> softmax -> P V' (forward) and dp -> ds -> dq (reverse) need no CTA-wide barrier in between
+// and all 8 warps work on every chunk even when the CTA holds only two samples.
+template <class C>
+struct AttnMap {
+    static constexpr int LPR = (C::kPN <= 16) ? 16 : 32;
+    static constexpr int DPL = 64 / LPR;
+    static constexpr int UPW = 32 / LPR;              // rows per warp and round
+};
+template <int LPR>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+template <int LPR>
+__device__ __forceinline__ float group_max(float v) {
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float dot64(const float* __restrict__ a, const float* __restrict__ b) {
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+        const float4 x = *reinterpret_cast<const float4*>(a + 4 * t), y = *reinterpret_cast<const float4*>(b + 4 * t);
+        d0 = fmaf(x.x, y.x, d0); d1 = fmaf(x.y, y.y, d1); d2 = fmaf(x.z, y.z, d2); d3 = fmaf(x.w, y.w, d3);
+    }
+    return (d0 + d1) + (d2 + d3);
+}
+// acc[e] (+)= sum_j w_j * src_j[e]  with w_j taken from lane (group base + j) of `wreg`
+template <int LPR, int DPL>
+__device__ __forceinline__ void group_weighted_rows(float (&acc)[DPL], float wreg, int gbase, const float* __restrict__ src, int ld, int N) {
+    for (int j = 0; j < N; ++j) {
+        const float w = __shfl_sync(0xffffffffu, wreg, gbase + j);
+        if (DPL == 4) {
+            const float4 v = *reinterpret_cast<const float4*>(src + j * ld);
+            acc[0] = fmaf(w, v.x, acc[0]); acc[1] = fmaf(w, v.y, acc[1]); acc[2 % DPL] = fmaf(w, v.z, acc[2 % DPL]); acc[3 % DPL] = fmaf(w, v.w, acc[3 % DPL]);
+        } else {
+            const float2 v = *reinterpret_cast<const float2*>(src + j * ld);
+            acc[0] = fmaf(w, v.x, acc[0]); acc[1] = fmaf(w, v.y, acc[1]);
+        }
+    }
+}
+template <int DPL>
+__device__ __forceinline__ void can_store_group(float* hi, float* lo, int row, int sub, const float (&v)[DPL]) {
+    if (DPL == 4) can_store4(hi, lo, row, sub, make_float4(v[0], v[1], v[2 % DPL], v[3 % DPL]));
+    else can_store2(hi, lo, row, 2 * sub, v[0], v[1]);
+}
+
+// Forward for head chunk hc: p_u. = softmax_j(s q_u . k'_j), o_u = sum_j p_uj v'_j - A x_u + c -> canonical slot; p -> stash.
+template <class C>
+__device__ __forceinline__ void attn_forward_rows(Ctx2& c, const LayerDev& W, int hc, int N, int NP, float* st_p) {
+    using AM = AttnMap<C>;
+    constexpr int LPR = AM::LPR, DPL = AM::DPL;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane % LPR, gbase = lane - sub;
+    const int rows = c.rows_act;
+    float cc[DPL], ax[DPL][3];
+#pragma unroll
+    for (int e = 0; e < DPL; ++e) {
+        const int col = hc * 64 + sub * DPL + e;
+        cc[e] = __ldg(W.cvec + col);
+        const float4 a4 = __ldg(reinterpret_cast<const float4*>(W.A + col * 4));
+        ax[e][0] = a4.x; ax[e][1] = a4.y; ax[e][2] = a4.z;
+    }
+    for (int base = warp * AM::UPW; base < rows; base += kWarps * AM::UPW) {
+        const int u0 = base + lane / LPR;
+        const bool valid = u0 < rows;
+        const int u = valid ? u0 : rows - 1;
+        const int r0 = (u / N) * N;
+        const bool act = sub < N;
+        const float dot = dot64(c.sQKV + u * C::LDQ, c.sQKV + (r0 + min(sub, N - 1)) * C::LDQ + 64);
+        const float lg = act ? kAttnScale * dot : -INFINITY;
+        const float m = group_max<LPR>(lg);
+        const float e = act ? expf(lg - m) : 0.f;
+        const float p = e / group_sum<LPR>(e);
+        if (valid && sub < NP) st_p[(size_t)u * NP + sub] = p;
+        float acc[DPL];
+#pragma unroll
+        for (int e2 = 0; e2 < DPL; ++e2) acc[e2] = 0.f;
+        group_weighted_rows<LPR, DPL>(acc, p, gbase, c.sQKV + r0 * C::LDQ + 128 + sub * DPL, C::LDQ, N);
+        const float x0 = c.sX[u * 4], x1 = c.sX[u * 4 + 1], x2 = c.sX[u * 4 + 2];
+#pragma unroll
+        for (int e2 = 0; e2 < DPL; ++e2) acc[e2] += cc[e2] - (ax[e2][0] * x0 + ax[e2][1] * x1 + ax[e2][2] * x2);
+        c.slot_acquire();      // the previous out-projection has had the whole row computation to finish reading the slot
+        if (valid) can_store_group<DPL>(c.slot_hi, c.slot_lo, u, sub, acc);
+    }
+}
+
+// Reverse pass A for query row u: dp_uj = do_u . v'_j, ds_uj = p_uj (dp_uj - sum_j p_uj dp_uj) -> sDS;
+// layers > 0 also dq_u = s sum_j ds_uj k'_j -> canonical slot.
+template <class C>
+__device__ __forceinline__ void attn_backward_ds_dq(Ctx2& c, int N, int NP, bool want_dq) {
+    using AM = AttnMap<C>;
+    constexpr int LPR = AM::LPR, DPL = AM::DPL;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane % LPR, gbase = lane - sub;
+    const int rows = c.rows_act;
+    for (int base = warp * AM::UPW; base < rows; base += kWarps * AM::UPW) {
+        const int u0 = base + lane / LPR;
+        const bool valid = u0 < rows;
+        const int u = valid ? u0 : rows - 1;
+        const int r0 = (u / N) * N;
+        const bool act = sub < N;
+        const float dp = dot64(c.sO + u * C::LDO, c.sQKV + (r0 + min(sub, N - 1)) * C::LDQ + 128);
+        const float p = act ? c.sP[u * NP + sub] : 0.f;
+        const float ds = p * (dp - group_sum<LPR>(p * dp));
+        if (valid && sub < NP) c.sDS[u * NP + sub] = ds;
+        if (want_dq) {
+            float acc[DPL];
+#pragma unroll
+            for (int e = 0; e < DPL; ++e) acc[e] = 0.f;
+            group_weighted_rows<LPR, DPL>(acc, ds, gbase, c.sQKV + r0 * C::LDQ + 64 + sub * DPL, C::LDQ, N);
+#pragma unroll
+            for (int e = 0; e < DPL; ++e) acc[e] *= kAttnScale;
+            c.slot_acquire();
+            if (valid) can_store_group<DPL>(c.slot_hi, c.slot_lo, u, sub, acc);
+        }
+    }
+}
+// Reverse passes B / C for key row u (= s*N + j), lanes over output columns:
+//   dk'_u = s sum_i ds_iu q_i   -> slot (job d k');   dv'_u = sum_i p_iu do_i   -> slot (job d v');
+//   dx_u += A_h^T (dk'_u + dv'_u - do_u)
+// Both products are formed in registers first, so that the single rotating slot is only waited for when its previous
+// job (d q, then d k') has had a whole computation phase to complete.
+template <class C>
+__device__ __forceinline__ void attn_backward_dkv(Ctx2& c, const LayerDev& W, int hc, int N, int NP, bool to_slot) {
+    using AM = AttnMap<C>;
+    constexpr int LPR = AM::LPR, DPL = AM::DPL;
+    constexpr int MR = C::kR / (kWarps * AM::UPW);          // rounds a warp can have
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane % LPR;
+    const int rows = c.rows_act;
+    float ax[DPL][3];
+#pragma unroll
+    for (int e = 0; e < DPL; ++e) {
+        const float4 a4 = __ldg(reinterpret_cast<const float4*>(W.A + (hc * 64 + sub * DPL + e) * 4));
+        ax[e][0] = a4.x; ax[e][1] = a4.y; ax[e][2] = a4.z;
+    }
+    float dk[MR][DPL], dv[MR][DPL];
+#pragma unroll
+    for (int rd = 0; rd < MR; ++rd) {
+        const int base = (warp + rd * kWarps) * AM::UPW;
+#pragma unroll
+        for (int e = 0; e < DPL; ++e) { dk[rd][e] = 0.f; dv[rd][e] = 0.f; }
+        if (base < rows) {
+            const int u = min(base + lane / LPR, rows - 1);
+            const int r0 = (u / N) * N, jj = u - r0;
+            const float* wk = c.sDS + r0 * NP + jj;
+            const float* wv = c.sP + r0 * NP + jj;
+            const float* qs = c.sQKV + r0 * C::LDQ + sub * DPL;
+            const float* os = c.sO + r0 * C::LDO + sub * DPL;
+            for (int i = 0; i < N; ++i) {
+                const float a = wk[i * NP], b = wv[i * NP];
+                if (DPL == 4) {
+                    const float4 q = *reinterpret_cast<const float4*>(qs + i * C::LDQ), o = *reinterpret_cast<const float4*>(os + i * C::LDO);
+                    dk[rd][0] = fmaf(a, q.x, dk[rd][0]); dk[rd][1] = fmaf(a, q.y, dk[rd][1]);
+                    dk[rd][2 % DPL] = fmaf(a, q.z, dk[rd][2 % DPL]); dk[rd][3 % DPL] = fmaf(a, q.w, dk[rd][3 % DPL]);
+                    dv[rd][0] = fmaf(b, o.x, dv[rd][0]); dv[rd][1] = fmaf(b, o.y, dv[rd][1]);
+                    dv[rd][2 % DPL] = fmaf(b, o.z, dv[rd][2 % DPL]); dv[rd][3 % DPL] = fmaf(b, o.w, dv[rd][3 % DPL]);
+                } else {
+                    const float2 q = *reinterpret_cast<const float2*>(qs + i * C::LDQ), o = *reinterpret_cast<const float2*>(os + i * C::LDO);
+                    dk[rd][0] = fmaf(a, q.x, dk[rd][0]); dk[rd][1] = fmaf(a, q.y, dk[rd][1]);
+                    dv[rd][0] = fmaf(b, o.x, dv[rd][0]); dv[rd][1] = fmaf(b, o.y, dv[rd][1]);
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < DPL; ++e) dk[rd][e] *= kAttnScale;
+        }
+    }
+    if (to_slot) {          // job d k'
+        c.slot_acquire();
+#pragma unroll
+        for (int rd = 0; rd < MR; ++rd) {
+            const int u0 = (warp + rd * kWarps) * AM::UPW + lane / LPR;
+            if (u0 < rows) can_store_group<DPL>(c.slot_hi, c.slot_lo, u0, sub, dk[rd]);
+        }
+        c.slot_post();
+    }
+    // dx_u += A_h^T (dk'_u + dv'_u - do_u): runs while the tensor core consumes d k'
+#pragma unroll
+    for (int rd = 0; rd < MR; ++rd) {
+        const int base = (warp + rd * kWarps) * AM::UPW;
+        if (base < rows) {
+            const int u0 = base + lane / LPR;
+            const int u = min(u0, rows - 1);
+            float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+#pragma unroll
+            for (int e = 0; e < DPL; ++e) {
+                const float t = dk[rd][e] + dv[rd][e] - c.sO[u * C::LDO + sub * DPL + e];
+                g0 = fmaf(ax[e][0], t, g0); g1 = fmaf(ax[e][1], t, g1); g2 = fmaf(ax[e][2], t, g2);
+            }
+            g0 = group_sum<LPR>(g0); g1 = group_sum<LPR>(g1); g2 = group_sum<LPR>(g2);
+            if (u0 < rows && sub == 0) { c.sDX[u * 4] += g0; c.sDX[u * 4 + 1] += g1; c.sDX[u * 4 + 2] += g2; }
+        }
+    }
+    if (to_slot) {          // job d v'
+        c.slot_acquire();
+#pragma unroll
+        for (int rd = 0; rd < MR; ++rd) {
+            const int u0 = (warp + rd * kWarps) * AM::UPW + lane / LPR;
+            if (u0 < rows) can_store_group<DPL>(c.slot_hi, c.slot_lo, u0, sub, dv[rd]);
+        }
+        c.slot_post();
+    } else {
+        csync();
+    }
+}
+
+// FF hidden block [rows][4H] TMEM -> shared (row stride LDF), so that the GELU phases can be spread over all threads
+constexpr int kLDF = 256 + 4;
+
 // ------------------------------------------------------------------ forward pass (compute warps)
 template <class C>
 __device__ void forward_pass_tc(const ModelDev& M, Ctx2& c, float t_norm) {
     constexpr int R = C::kR;
     const int tid = threadIdx.x;
     const int N = M.N, NP = M.NP, H = M.H;
+    const int rows = c.rows_act;
 
     // layer-0 node stream: W_n [onehot_i, t] + b_n   (graph_transformer.py:99-103)
-    for (int idx = tid; idx < R * C::kHP; idx += kThreads) {
+    for (int idx = tid; idx < rows * C::kHP; idx += kThreads) {
         const int r = idx / C::kHP, d = idx - r * C::kHP;
-        float v = 0.f;
-        if (r < c.rows_act) v = __ldg(M.emb + (r % N) * H + d) + t_norm * __ldg(M.embt + d);
-        c.sN[r * C::LDH + d] = v;
+        c.sN[r * C::LDH + d] = __ldg(M.emb + (r % N) * H + d) + t_norm * __ldg(M.embt + d);
     }
     // augmented operand columns of this step: [x0 x1 x2 1] (chunk H/4); chunk H/4 + 1 stays zero
     if (tid < R) {
-        const float4 xv = (tid < c.rows_act) ? make_float4(c.sX[tid * 4], c.sX[tid * 4 + 1], c.sX[tid * 4 + 2], 1.0f)
-                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 xv = (tid < rows) ? make_float4(c.sX[tid * 4], c.sX[tid * 4 + 1], c.sX[tid * 4 + 2], 1.0f)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
         can_store4(c.nhat_hi, c.nhat_lo, tid, C::kHP / 4, xv);
     }
     csync();
-    ln_forward_rows_can<C>(c.sN, c.nhat_hi, c.nhat_lo, M.layer[0].ln1_g, M.layer[0].ln1_b, H, c.stash + M.off[ST_NIN],
+    ln_forward_rows_can<C>(c.sN, c.nhat_hi, c.nhat_lo, M.layer[0].ln1_g, M.layer[0].ln1_b, H, rows, c.stash + M.off[ST_NIN],
                            c.stash + M.off[ST_STAT1]);
     c.post();
+    c.mark(0);
 
     for (int l = 0; l < M.L; ++l) {
         const LayerDev& W = M.layer[l];
@@ -347,8 +606,9 @@ __device__ void forward_pass_tc(const ModelDev& M, Ctx2& c, float t_norm) {
         for (int hc = 0; hc < C::NCH; ++hc) {
             {   // q | k' | v' of the head chunk: TMEM -> shared (row-major, for the attention) + stash
                 const int b = c.dq_wait();
+                c.mark(1);
                 float* st_qkv = st + M.off[ST_QKV] + (size_t)hc * R * 3 * C::CWQ;
-                tmem_foreach<192>(c.tmem, kColD + b * 192, [&](int row, int col, const float (&v)[16]) {
+                tmem_foreach<192>(c.tmem, kColD + b * 192, rows, [&](int row, int col, const float (&v)[16]) {
 #pragma unroll
                     for (int i = 0; i < 16; i += 4) {
                         const float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
@@ -357,36 +617,18 @@ __device__ void forward_pass_tc(const ModelDev& M, Ctx2& c, float t_norm) {
                     }
                 });
                 c.dq_release();
+                c.mark(2);
             }
-            attn_nt(c.sQKV, C::LDQ, c.sQKV + C::CWQ, C::LDQ, c.sP, R * NP, NP, N, c.S_act, 1, kAttnScale);
-            csync();
-            softmax_rows<R, 1>(c.sP, NP, N, c.rows_act);
-            csync();
-            {
-                float* dst = st + M.off[ST_P] + (size_t)hc * R * NP;
-                for (int idx = tid; idx < (R * NP) / 4; idx += kThreads)
-                    reinterpret_cast<float4*>(dst)[idx] = reinterpret_cast<const float4*>(c.sP)[idx];
-            }
-            // o_i = sum_j p_ij v'_j - A x_i + c  -> canonical operand of the out-projection
-            attn_pv<false>(c.sP, R * NP, NP, c.sQKV + 2 * C::CWQ, C::LDQ, N, c.S_act, 1,
-                           [&](int, int s, int i, int d, const float4& a) {
-                const int row = s * N + i;
-                const float x0 = c.sX[row * 4], x1 = c.sX[row * 4 + 1], x2 = c.sX[row * 4 + 2];
-                const float4 cc = __ldg(reinterpret_cast<const float4*>(W.cvec + hc * C::CWQ + d));
-                float o[4] = {a.x + cc.x, a.y + cc.y, a.z + cc.z, a.w + cc.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float4 a4 = __ldg(reinterpret_cast<const float4*>(W.A + (hc * C::CWQ + d + e) * 4));
-                    o[e] -= a4.x * x0 + a4.y * x1 + a4.z * x2;
-                }
-                c.slot_acquire();
-                can_store4(c.slot_hi, c.slot_lo, row, d >> 2, make_float4(o[0], o[1], o[2], o[3]));
-            });
+            // logits, softmax, P V' - A x_i + c -> canonical operand of the out-projection (row-local, no barrier inside)
+            attn_forward_rows<C>(c, W, hc, N, NP, st + M.off[ST_P] + (size_t)hc * R * NP);
+            c.mark(3);
             c.slot_post();
+            c.mark(4);
         }
         // attention block output -> row buffer; gated residual 1 + LayerNorm 2 -> canonical operand of FF1
         c.acc_wait();
-        tmem_foreach<64>(c.tmem, kColAcc, [&](int row, int col, const float (&v)[16]) {
+        c.mark(5);
+        tmem_foreach<64>(c.tmem, kColAcc, rows, [&](int row, int col, const float (&v)[16]) {
 #pragma unroll
             for (int i = 0; i < 16; i += 4) {
                 const float4 b = __ldg(reinterpret_cast<const float4*>(W.bo + col + i));
@@ -395,38 +637,52 @@ __device__ void forward_pass_tc(const ModelDev& M, Ctx2& c, float t_norm) {
         });
         tc::fence_before_sync();
         csync();
-        gate_ln_forward_rows_can<C>(c.sN, c.sNh, c.nhat_hi, c.nhat_lo, W.g1a, W.g1b, H, st + M.off[ST_ATT], st + M.off[ST_G1],
+        c.mark(6);
+        gate_ln_forward_rows_can<C>(c.sN, c.sNh, c.nhat_hi, c.nhat_lo, W.g1a, W.g1b, H, rows, st + M.off[ST_ATT], st + M.off[ST_G1],
                                     st + M.off[ST_M], W.ln2_g, W.ln2_b, st + M.off[ST_STAT2]);
         c.post();
+        c.mark(7);
 
-        // feed-forward: hidden pre-activations [R][4H] sit in TMEM; GELU 64 columns at a time -> slot -> FF2 accumulates
+        // feed-forward: hidden pre-activations [rows][4H] TMEM -> shared once; then bias + GELU 64 columns at a time,
+        // spread over all threads -> slot -> FF2 accumulates
         c.d1_wait();
-        {
-            const int warp = tid >> 5, lane = tid & 31;
-            const int q = warp & 3, part = warp >> 2, row = q * 16 + lane;
-            const uint32_t taddr = c.tmem + ((uint32_t)(q * 32) << 16) + kColD;
-            for (int ch = 0; ch < 4; ++ch) {
-                float v[2][16];
-                tmem_ld16(taddr + (uint32_t)(ch * 64 + part * 32), v[0]);
-                tmem_ld16(taddr + (uint32_t)(ch * 64 + part * 32 + 16), v[1]);
-                if (lane < 16) {
+        c.mark(8);
+        float* sH = c.sQKV;
+        tmem_foreach<256>(c.tmem, kColD, rows, [&](int row, int col, const float (&v)[16]) {
 #pragma unroll
-                    for (int u = 0; u < 2; ++u)
+            for (int i = 0; i < 16; i += 4)
+                *reinterpret_cast<float4*>(sH + row * kLDF + col + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        });
+        tc::fence_before_sync();
+        csync();
+        c.mark(9);
+        for (int ch = 0; ch < 4; ++ch) {
+            constexpr int MG = (R * 16) / kThreads;       // granules (row, 4 columns) per thread
+            float4 gq[MG];
 #pragma unroll
-                        for (int i = 0; i < 16; i += 4) {
-                            const int cl = part * 32 + u * 16 + i;          // column inside the 64-wide chunk
-                            const float4 b = __ldg(reinterpret_cast<const float4*>(W.b1 + ch * 64 + cl));
-                            const float4 pre = make_float4(v[u][i] + b.x, v[u][i + 1] + b.y, v[u][i + 2] + b.z, v[u][i + 3] + b.w);
-                            *reinterpret_cast<float4*>(st + M.off[ST_H1] + (size_t)row * (4 * H) + ch * 64 + cl) = pre;
-                            c.slot_acquire();
-                            can_store4(c.slot_hi, c.slot_lo, row, cl >> 2, make_float4(gelu_f(pre.x), gelu_f(pre.y), gelu_f(pre.z), gelu_f(pre.w)));
-                        }
+            for (int g = 0; g < MG; ++g) {
+                const int idx = tid + g * kThreads;
+                if (idx < rows * 16) {
+                    const int r = idx >> 4, k4 = idx & 15;
+                    const float4 v = *reinterpret_cast<const float4*>(sH + r * kLDF + ch * 64 + k4 * 4);
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(W.b1 + ch * 64 + k4 * 4));
+                    const float4 pre = make_float4(v.x + b.x, v.y + b.y, v.z + b.z, v.w + b.w);
+                    *reinterpret_cast<float4*>(st + M.off[ST_H1] + (size_t)r * (4 * H) + ch * 64 + k4 * 4) = pre;
+                    gq[g] = make_float4(gelu_f(pre.x), gelu_f(pre.y), gelu_f(pre.z), gelu_f(pre.w));
                 }
-                c.slot_post();
             }
+            c.slot_acquire();
+#pragma unroll
+            for (int g = 0; g < MG; ++g) {
+                const int idx = tid + g * kThreads;
+                if (idx < rows * 16) can_store4(c.slot_hi, c.slot_lo, idx >> 4, idx & 15, gq[g]);
+            }
+            c.slot_post();
         }
+        c.mark(10);
         c.acc_wait();
-        tmem_foreach<64>(c.tmem, kColAcc, [&](int row, int col, const float (&v)[16]) {
+        c.mark(5);
+        tmem_foreach<64>(c.tmem, kColAcc, rows, [&](int row, int col, const float (&v)[16]) {
 #pragma unroll
             for (int i = 0; i < 16; i += 4) {
                 const float4 b = __ldg(reinterpret_cast<const float4*>(W.b2 + col + i));
@@ -438,10 +694,11 @@ __device__ void forward_pass_tc(const ModelDev& M, Ctx2& c, float t_norm) {
         // gated residual 2 (+ next layer's LayerNorm 1; its input rows are the next layer's n_in stash)
         const bool last = (l + 1 == M.L);
         float* stn = st + M.layer_floats;
-        gate_ln_forward_rows_can<C>(c.sN, c.sNh, c.nhat_hi, c.nhat_lo, W.g2a, W.g2b, H, st + M.off[ST_FF], st + M.off[ST_G2],
+        gate_ln_forward_rows_can<C>(c.sN, c.sNh, c.nhat_hi, c.nhat_lo, W.g2a, W.g2b, H, rows, st + M.off[ST_FF], st + M.off[ST_G2],
                                     stn + M.off[ST_NIN], last ? nullptr : M.layer[l + 1].ln1_g,
                                     last ? nullptr : M.layer[l + 1].ln1_b, last ? nullptr : stn + M.off[ST_STAT1]);
         if (!last) c.post(); else csync();
+        c.mark(7);
     }
 }
 
@@ -451,8 +708,9 @@ __device__ void backward_pass_tc(const ModelDev& M, Ctx2& c) {
     constexpr int R = C::kR;
     const int tid = threadIdx.x;
     const int N = M.N, NP = M.NP, H = M.H;
+    const int rows = c.rows_act;
 
-    for (int idx = tid; idx < R * C::kHP; idx += kThreads) {
+    for (int idx = tid; idx < rows * C::kHP; idx += kThreads) {
         const int r = idx / C::kHP, d = idx - r * C::kHP;
         c.sN[r * C::LDH + d] = __ldg(M.dec_w + d);               // dE_r/dn_r = w_dec  (node_decoder, :106)
     }
@@ -464,49 +722,47 @@ __device__ void backward_pass_tc(const ModelDev& M, Ctx2& c) {
         float* st = c.stash + (size_t)l * M.layer_floats;
 
         // gated residual 2 backward: d ff -> canonical operand, d m (partial) -> sN
-        gate_backward_rows_can<C>(c.sN, nullptr, c.nhat_hi, c.nhat_lo, H, nullptr, nullptr, nullptr, st + M.off[ST_FF],
+        gate_backward_rows_can<C>(c.sN, nullptr, c.nhat_hi, c.nhat_lo, H, rows, nullptr, nullptr, nullptr, st + M.off[ST_FF],
                                   st + M.off[ST_M], st + M.off[ST_G2], W.g2a, W.g2b);
         c.post();
-        // feed-forward backward: d act [R][4H] in TMEM; times GELU' 64 columns at a time -> slot -> d m_hat accumulates
-        {
-            const int warp = tid >> 5, lane = tid & 31;
-            const int q = warp & 3, part = warp >> 2, row = q * 16 + lane;
-            const uint32_t taddr = c.tmem + ((uint32_t)(q * 32) << 16) + kColD;
-            float4 pre[2][4];
-            auto fetch = [&](int ch) {       // stash loads of the chunk's pre-activations, issued ahead of their use
-                if (lane < 16) {
+        c.mark(11);
+        // feed-forward backward: d act [rows][4H] TMEM -> shared once; times GELU'(pre) 64 columns at a time -> slot
+        c.d1_wait();
+        c.mark(8);
+        float* sH = c.sQKV;
+        tmem_foreach<256>(c.tmem, kColD, rows, [&](int row, int col, const float (&v)[16]) {
 #pragma unroll
-                    for (int u = 0; u < 2; ++u)
+            for (int i = 0; i < 16; i += 4)
+                *reinterpret_cast<float4*>(sH + row * kLDF + col + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        });
+        tc::fence_before_sync();
+        csync();
+        c.mark(12);
+        for (int ch = 0; ch < 4; ++ch) {
+            constexpr int MG = (R * 16) / kThreads;
+            float4 gq[MG];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            pre[u][i] = *reinterpret_cast<const float4*>(st + M.off[ST_H1] + (size_t)row * (4 * H) + ch * 64 + part * 32 + u * 16 + i * 4);
+            for (int g = 0; g < MG; ++g) {
+                const int idx = tid + g * kThreads;
+                if (idx < rows * 16) {
+                    const int r = idx >> 4, k4 = idx & 15;
+                    const float4 p = *reinterpret_cast<const float4*>(st + M.off[ST_H1] + (size_t)r * (4 * H) + ch * 64 + k4 * 4);
+                    const float4 v = *reinterpret_cast<const float4*>(sH + r * kLDF + ch * 64 + k4 * 4);
+                    gq[g] = make_float4(v.x * gelu_grad_f(p.x), v.y * gelu_grad_f(p.y), v.z * gelu_grad_f(p.z), v.w * gelu_grad_f(p.w));
                 }
-            };
-            fetch(0);
-            c.d1_wait();
-            for (int ch = 0; ch < 4; ++ch) {
-                float v[2][16];
-                tmem_ld16(taddr + (uint32_t)(ch * 64 + part * 32), v[0]);
-                tmem_ld16(taddr + (uint32_t)(ch * 64 + part * 32 + 16), v[1]);
-                if (lane < 16) {
-                    c.slot_acquire();
-#pragma unroll
-                    for (int u = 0; u < 2; ++u)
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int cl = part * 32 + u * 16 + i * 4;
-                            const float4 p = pre[u][i];
-                            can_store4(c.slot_hi, c.slot_lo, row, cl >> 2,
-                                       make_float4(v[u][i * 4] * gelu_grad_f(p.x), v[u][i * 4 + 1] * gelu_grad_f(p.y),
-                                                   v[u][i * 4 + 2] * gelu_grad_f(p.z), v[u][i * 4 + 3] * gelu_grad_f(p.w)));
-                        }
-                }
-                if (ch + 1 < 4) fetch(ch + 1);
-                c.slot_post();
             }
+            c.slot_acquire();
+#pragma unroll
+            for (int g = 0; g < MG; ++g) {
+                const int idx = tid + g * kThreads;
+                if (idx < rows * 16) can_store4(c.slot_hi, c.slot_lo, idx >> 4, idx & 15, gq[g]);
+            }
+            c.slot_post();
         }
+        c.mark(13);
         c.acc_wait();
-        tmem_foreach<64>(c.tmem, kColAcc, [&](int row, int col, const float (&v)[16]) {
+        c.mark(5);
+        tmem_foreach<64>(c.tmem, kColAcc, rows, [&](int row, int col, const float (&v)[16]) {
 #pragma unroll
             for (int i = 0; i < 16; i += 4)
                 *reinterpret_cast<float4*>(c.sNh + row * C::LDH + col + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
@@ -514,87 +770,54 @@ __device__ void backward_pass_tc(const ModelDev& M, Ctx2& c) {
         tc::fence_before_sync();
         csync();
         // LayerNorm 2 backward + gated residual 1 backward: d att -> canonical operand, d n_in (residual part) -> sN
-        gate_backward_rows_can<C>(c.sN, c.sNh, c.nhat_hi, c.nhat_lo, H, W.ln2_g, st + M.off[ST_M], st + M.off[ST_STAT2],
+        gate_backward_rows_can<C>(c.sN, c.sNh, c.nhat_hi, c.nhat_lo, H, rows, W.ln2_g, st + M.off[ST_M], st + M.off[ST_STAT2],
                                   st + M.off[ST_ATT], st + M.off[ST_NIN], st + M.off[ST_G1], W.g1a, W.g1b);
         c.post();
+        c.mark(14);
 
         for (int hc = 0; hc < C::NCH; ++hc) {
             // start reloading q | k' | v' and p of this chunk; the copies land while d o is read back
-            stash_load_async<R>(c.sQKV, C::LDQ, st + M.off[ST_QKV] + (size_t)hc * R * 3 * C::CWQ, 3 * C::CWQ);
             {
-                const float* src = st + M.off[ST_P] + (size_t)hc * R * NP;
-                for (int idx = tid; idx < (R * NP) / 4; idx += kThreads) cp_async16(c.sP + idx * 4, src + idx * 4);
+                const float* src = st + M.off[ST_QKV] + (size_t)hc * R * 3 * C::CWQ;
+                for (int idx = tid; idx < rows * 48; idx += kThreads) {
+                    const int r = idx / 48, c4 = idx - r * 48;
+                    cp_async16(c.sQKV + r * C::LDQ + c4 * 4, src + (size_t)r * 192 + c4 * 4);
+                }
+                const float* srcp = st + M.off[ST_P] + (size_t)hc * R * NP;
+                for (int idx = tid; idx < (rows * NP) / 4; idx += kThreads) cp_async16(c.sP + idx * 4, srcp + idx * 4);
             }
             {   // d o_chunk = d att x Wo_b[l][hc]: TMEM -> shared
+                c.mark(15);
                 const int b = c.dq_wait();
-                tmem_foreach<64>(c.tmem, kColD + b * 64, [&](int row, int col, const float (&v)[16]) {
+                c.mark(1);
+                tmem_foreach<64>(c.tmem, kColD + b * 64, rows, [&](int row, int col, const float (&v)[16]) {
 #pragma unroll
                     for (int i = 0; i < 16; i += 4)
                         *reinterpret_cast<float4*>(c.sO + row * C::LDO + col + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
                 });
                 cp_async_wait_all();
                 c.dq_release();
+                c.mark(16);
             }
-            // dp_ij = do_i . v'_j
-            attn_nt(c.sO, C::LDO, c.sQKV + 2 * C::CWQ, C::LDQ, c.sDS, R * NP, NP, N, c.S_act, 1, 1.0f);
-            csync();
-            softmax_backward_rows<R, 1>(c.sDS, c.sP, NP, N, c.rows_act);
-            csync();
-            if (l > 0) {   // dq_i = s sum_j ds_ij k'_j  -> slot (operand of the Wq^T job)
-                attn_pv<false>(c.sDS, R * NP, NP, c.sQKV + C::CWQ, C::LDQ, N, c.S_act, 1,
-                               [&](int, int s, int i, int d, const float4& a) {
-                    c.slot_acquire();
-                    can_store4(c.slot_hi, c.slot_lo, s * N + i, d >> 2,
-                               make_float4(kAttnScale * a.x, kAttnScale * a.y, kAttnScale * a.z, kAttnScale * a.w));
-                });
-                c.slot_post();
-            }
-            // dk'_j = s sum_i ds_ij q_i  -> k' columns (k' is dead after dq) and slot (operand of the Wk^T job)
-            attn_pv<true>(c.sDS, R * NP, NP, c.sQKV, C::LDQ, N, c.S_act, 1, [&](int, int s, int j, int d, const float4& a) {
-                const float4 o = make_float4(kAttnScale * a.x, kAttnScale * a.y, kAttnScale * a.z, kAttnScale * a.w);
-                *reinterpret_cast<float4*>(c.sQKV + (s * N + j) * C::LDQ + C::CWQ + d) = o;
-                if (l > 0) { c.slot_acquire(); can_store4(c.slot_hi, c.slot_lo, s * N + j, d >> 2, o); }
-            });
-            if (l > 0) c.slot_post(); else csync();
-            // dv'_j = sum_i p_ij do_i  -> q columns (q is dead after dk') and slot (operand of the Wv^T job)
-            attn_pv<true>(c.sP, R * NP, NP, c.sO, C::LDO, N, c.S_act, 1, [&](int, int s, int j, int d, const float4& a) {
-                *reinterpret_cast<float4*>(c.sQKV + (s * N + j) * C::LDQ + d) = a;
-                if (l > 0) { c.slot_acquire(); can_store4(c.slot_hi, c.slot_lo, s * N + j, d >> 2, a); }
-            });
-            if (l > 0) c.slot_post(); else csync();
-            // dx_r += A_h^T (dk'_r + dv'_r - do_r)   (fixed summation order: deterministic)
-            for (int idx = tid; idx < c.rows_act * 3; idx += kThreads) {
-                const int r = idx / 3, cc = idx - r * 3;
-                float s = 0.f;
-                const float* dk = c.sQKV + r * C::LDQ + C::CWQ;
-                const float* dv = c.sQKV + r * C::LDQ;
-                const float* dO = c.sO + r * C::LDO;
-                const float* Ah = W.A + (hc * C::CWQ) * 4 + cc;
-#pragma unroll 4
-                for (int d = 0; d < 64; d += 4) {
-                    const float4 a = *reinterpret_cast<const float4*>(dk + d);
-                    const float4 b = *reinterpret_cast<const float4*>(dv + d);
-                    const float4 o = *reinterpret_cast<const float4*>(dO + d);
-                    s = fmaf(__ldg(Ah + (d + 0) * 4), a.x + b.x - o.x, s);
-                    s = fmaf(__ldg(Ah + (d + 1) * 4), a.y + b.y - o.y, s);
-                    s = fmaf(__ldg(Ah + (d + 2) * 4), a.z + b.z - o.z, s);
-                    s = fmaf(__ldg(Ah + (d + 3) * 4), a.w + b.w - o.w, s);
-                }
-                c.sDX[r * 4 + cc] += s;
-            }
-            csync();
+            attn_backward_ds_dq<C>(c, N, NP, l > 0);
+            c.mark(17);
+            if (l > 0) c.slot_post(); else csync();          // every ds of the sample is in sDS before the key-row passes
+            c.mark(18);
+            attn_backward_dkv<C>(c, W, hc, N, NP, l > 0);
+            c.mark(19);
         }
         if (l > 0) {
             c.acc_wait();
-            tmem_foreach<64>(c.tmem, kColAcc, [&](int row, int col, const float (&v)[16]) {
+            tmem_foreach<64>(c.tmem, kColAcc, rows, [&](int row, int col, const float (&v)[16]) {
 #pragma unroll
                 for (int i = 0; i < 16; i += 4)
                     *reinterpret_cast<float4*>(c.sNh + row * C::LDH + col + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
             });
             tc::fence_before_sync();
             csync();
-            ln_backward_rows<C>(c.sN, c.sNh, H, W.ln1_g, st + M.off[ST_NIN], st + M.off[ST_STAT1]);
+            ln_backward_rows_tc<C>(c.sN, c.sNh, H, rows, W.ln1_g, st + M.off[ST_NIN], st + M.off[ST_STAT1]);
             csync();
+            c.mark(21);
         }
     }
 }
@@ -642,23 +865,29 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
         // ===================================================== TMA producer: streams the weight slices of every job
         if ((tid & 31) == 0) {
             uint32_t slice_i = 0;
+            long long pw[1] = {0};
             for (uint32_t rep = 0; rep < reps; ++rep)
                 for (int j = 0; j < njobs; ++j) {
                     const TcJob jb = jobs[j];
                     const char* src = reinterpret_cast<const char*>(jb.base);
                     for (uint32_t s = 0; s < jb.n_slices; ++s, ++slice_i) {
                         const uint32_t stg = slice_i % kTcStages, use = slice_i / kTcStages;
-                        if (use > 0) mbar_wait_wd(bars + B_EMPTY + stg, (use - 1) & 1u, 5);
+                        { TCP_BEGIN(); if (use > 0) mbar_wait_wd(bars + B_EMPTY + stg, (use - 1) & 1u, 5); TCP_END(pw, 0); }
                         mbar_expect_tx(bars + B_FULL + stg, jb.slice_bytes);
                         bulk_g2s(smem + C::oW + stg * kTcStageFloats, src + (size_t)s * jb.slice_bytes, jb.slice_bytes, bars + B_FULL + stg);
                     }
                 }
             (void)nslices;
+#ifdef DFF_TC_PROFILE
+            if (T.dbg) T.dbg[blockIdx.x * 16 + 8] = pw[0];
+#endif
         }
     } else if (warp == kComputeThreads / 32 + 1) {
         // ===================================================== MMA issuer: walks the job table, one thread
         if ((tid & 31) == 0) {
             uint32_t slice_i = 0, post_seq = 0, dq_idx = 0;
+            long long iw[4] = {0, 0, 0, 0};
+            const long long t_begin = clock64();
             const float* nhat_hi = smem + C::oNhatHi; const float* nhat_lo = smem + C::oNhatLo;
             const float* slot_hi = smem + C::oSlotHi; const float* slot_lo = smem + C::oSlotLo;
             for (uint32_t rep = 0; rep < reps; ++rep)
@@ -666,11 +895,11 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
                     const TcJob jb = jobs[j];
                     if (jb.wait_post) {
                         ++post_seq;
-                        spin_until(ctr, post_seq, 7);
+                        TCP_BEGIN(); spin_until(ctr, post_seq, 7); TCP_END(iw, 0);
                     }
                     uint32_t dcol = jb.d_col;
                     if (jb.dbuf) {
-                        if (dq_idx >= 2) spin_until(ctr + 1, dq_idx - 1, 8);
+                        TCP_BEGIN(); if (dq_idx >= 2) spin_until(ctr + 1, dq_idx - 1, 8); TCP_END(iw, 1);
                         dcol += (dq_idx & 1u) * jb.n;
                     }
                     tc::fence_after_sync();
@@ -682,7 +911,7 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
                     uint32_t acc = jb.acc_first;
                     for (uint32_t s = 0; s < jb.n_slices; ++s, ++slice_i) {
                         const uint32_t stg = slice_i % kTcStages, use = slice_i / kTcStages;
-                        mbar_wait_wd(bars + B_FULL + stg, use & 1u, 6);
+                        { TCP_BEGIN(); mbar_wait_wd(bars + B_FULL + stg, use & 1u, 6); TCP_END(iw, 2); }
                         tc::fence_after_sync();
                         const float* bhi = smem + C::oW + stg * kTcStageFloats;
                         const float* blo = bhi + (uint32_t)jb.ks * jb.n;
@@ -702,6 +931,12 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
                     if (jb.commit_acc) tc::commit(bars + B_ACC);
                     if (jb.commit_d1) tc::commit(bars + B_D1);
                 }
+#ifdef DFF_TC_PROFILE
+            if (T.dbg) { T.dbg[blockIdx.x * 16 + 9] = iw[0]; T.dbg[blockIdx.x * 16 + 10] = iw[1]; T.dbg[blockIdx.x * 16 + 11] = iw[2];
+                         T.dbg[blockIdx.x * 16 + 12] = clock64() - t_begin; }
+#else
+            (void)iw; (void)t_begin;
+#endif
         }
     } else {
         // ===================================================== compute warps
@@ -712,6 +947,12 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
         c.nhat_hi = smem + C::oNhatHi; c.nhat_lo = smem + C::oNhatLo; c.slot_hi = smem + C::oSlotHi; c.slot_lo = smem + C::oSlotLo;
         c.bars = bars; c.posted = ctr; c.drained = ctr + 1; c.tmem = tmem;
         c.n_post = c.n_drain = c.n_acc = c.n_d1 = c.n_slot = 0; c.slot_held = false;
+        for (int i = 0; i < 8; ++i) c.tw[i] = 0;
+        const long long t_begin = clock64();
+#ifdef DFF_TC_PROFILE
+        for (int i = 0; i < 32; ++i) c.ph[i] = 0;
+        c.last = t_begin;
+#endif
         c.stash = M.scratch + (size_t)blockIdx.x * M.scratch_per_cta;
 
         uint32_t flags = 0;
@@ -741,6 +982,7 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
                 const int it = A.t_start - step;
                 const float t_norm = (A.mode == MODE_DDPM) ? (float)it / (float)A.T : A.t_norm;
 
+                c.mark(22);
                 forward_pass_tc<C>(M, c, t_norm);
                 if (A.energy_out != nullptr) {   // node_decoder (graph_transformer.py:106)
                     const int lane = tid & 31;
@@ -860,6 +1102,12 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
             csync();
         }
         if (A.flags != nullptr && flags != 0) atomicOr(A.flags, flags);
+#ifdef DFF_TC_PROFILE
+        if (T.dbg && tid == 0) { for (int i = 0; i < 4; ++i) T.dbg[blockIdx.x * 16 + i] = c.tw[i]; T.dbg[blockIdx.x * 16 + 7] = clock64() - t_begin; }
+        if (T.dbg && tid == 0 && blockIdx.x == 0) for (int i = 0; i < 32; ++i) T.dbg[(size_t)gridDim.x * 16 + i] = c.ph[i];
+#else
+        (void)t_begin;
+#endif
     }
 
     // teardown: every MMA has completed (the compute warps waited on the last accumulator) before TMEM is freed
