@@ -30,7 +30,12 @@ namespace dff {
 namespace v2 {
 
 constexpr int kR = 64;                    // node rows per CTA pass = MMA M
-constexpr int kComputeThreads = 256;      // must equal dff::kThreads (the shared phase helpers stride by it)
+#ifndef DFF_TC_COMPUTE_WARPS
+#define DFF_TC_COMPUTE_WARPS 16
+#endif
+constexpr int kCW = DFF_TC_COMPUTE_WARPS;          // compute warps (multiple of 4: TMEM lane quarters)
+constexpr int kCT = kCW * 32;                      // compute threads
+constexpr int kComputeThreads = kCT;
 constexpr int kTcThreads = kComputeThreads + 64;   // + TMA producer warp + MMA issuer warp
 constexpr int kTcStages = 3;
 constexpr int kTcStageFloats = 4096;      // 16 KB: the largest slice, [hi|lo] x [8 k][256 n]
@@ -104,7 +109,7 @@ struct TcCfg {
 enum { B_FULL = 0, B_EMPTY = 3, B_DQ = 6, B_ACC = 8, B_D1 = 9, B_SLOT = 10, B_COUNT = 11 };
 
 // ------------------------------------------------------------------ small PTX helpers
-__device__ __forceinline__ void csync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 compute warps
+__device__ __forceinline__ void csync() { asm volatile("bar.sync 1, %0;" ::"n"(kCT) : "memory"); }   // the compute warps
 __device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
     uint32_t v;
     asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
@@ -160,17 +165,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 // D[64 x NCOLS] at TMEM column `col`: with M = 64 row m lives in lane (m % 16) + 32 * (m / 16), so compute warp w reads
-// lane quarter w & 3 (rows 16 (w & 3) .. + 15 in its lanes 0..15) and the column half w >> 2.
+// lane quarter w & 3 (rows 16 (w & 3) .. + 15 in its lanes 0..15) and the column part w >> 2.
 // f(row, col_in_tile, v[16]) is called by the lanes that own an active row (row < rows).
 template <int NCOLS, class F>
 __device__ __forceinline__ void tmem_foreach(uint32_t tmem_base, uint32_t col, int rows, F f) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int PARTS = kCW / 4;
+    static_assert(NCOLS % (16 * PARTS) == 0, "column split");
     const int q = warp & 3, part = warp >> 2;
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + col;
     const int row = q * 16 + lane;
     if (q * 16 >= rows) return;                    // warp-uniform: this lane quarter holds no active row
 #pragma unroll 1
-    for (int c = part * (NCOLS / 2); c < (part + 1) * (NCOLS / 2); c += 16) {
+    for (int c = part * (NCOLS / PARTS); c < (part + 1) * (NCOLS / PARTS); c += 16) {
         float v[16];
         tmem_ld16(taddr + (uint32_t)c, v);
         if (lane < 16 && row < rows) f(row, c, v);
@@ -257,7 +264,7 @@ template <class C>
 __device__ __forceinline__ void ln_forward_rows_can(const float* sN, float* hi, float* lo, const float* __restrict__ gam,
                                                     const float* __restrict__ bet, int H, int rows, float* st_rows, float* st_stats) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int r = warp; r < rows; r += kWarps) {
+    for (int r = warp; r < rows; r += kCW) {
         const int col = lane * 2;
         const float2 x = *reinterpret_cast<const float2*>(sN + r * C::LDH + col);
         const float mean = warp_sum(x.x + x.y) / (float)H;
@@ -279,7 +286,7 @@ __device__ __forceinline__ void gate_ln_forward_rows_can(float* sN, const float*
                                                          const float* __restrict__ gam, const float* __restrict__ bet,
                                                          float* st_stats) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int r = warp; r < rows; r += kWarps) {
+    for (int r = warp; r < rows; r += kCW) {
         const int col = lane * 2;
         const float2 a = *reinterpret_cast<const float2*>(sA + r * C::LDH + col);
         const float2 n = *reinterpret_cast<const float2*>(sN + r * C::LDH + col);
@@ -311,7 +318,7 @@ __device__ __forceinline__ void gate_backward_rows_can(float* sN, const float* s
                                                        const float* st_g, const float* __restrict__ ga,
                                                        const float* __restrict__ gb) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int r = warp; r < rows; r += kWarps) {
+    for (int r = warp; r < rows; r += kCW) {
         const int col = lane * 2;
         const float2 a = *reinterpret_cast<const float2*>(st_a + (size_t)r * H + col);
         const float2 n = *reinterpret_cast<const float2*>(st_n + (size_t)r * H + col);
@@ -342,7 +349,7 @@ template <class C>
 __device__ __forceinline__ void ln_backward_rows_tc(float* sN, const float* sD, int H, int rows, const float* __restrict__ gam,
                                                     const float* st_ln_in, const float* st_stats) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int r = warp; r < rows; r += kWarps) {
+    for (int r = warp; r < rows; r += kCW) {
         const int col = lane * 2;
         const float mean = st_stats[r * 2], rstd = st_stats[r * 2 + 1];
         const float2 xin = *reinterpret_cast<const float2*>(st_ln_in + (size_t)r * H + col);
@@ -427,7 +434,7 @@ __device__ __forceinline__ void attn_forward_rows(Ctx2& c, const LayerDev& W, in
         const float4 a4 = __ldg(reinterpret_cast<const float4*>(W.A + col * 4));
         ax[e][0] = a4.x; ax[e][1] = a4.y; ax[e][2] = a4.z;
     }
-    for (int base = warp * AM::UPW; base < rows; base += kWarps * AM::UPW) {
+    for (int base = warp * AM::UPW; base < rows; base += kCW * AM::UPW) {
         const int u0 = base + lane / LPR;
         const bool valid = u0 < rows;
         const int u = valid ? u0 : rows - 1;
@@ -460,7 +467,7 @@ __device__ __forceinline__ void attn_backward_ds_dq(Ctx2& c, int N, int NP, bool
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane % LPR, gbase = lane - sub;
     const int rows = c.rows_act;
-    for (int base = warp * AM::UPW; base < rows; base += kWarps * AM::UPW) {
+    for (int base = warp * AM::UPW; base < rows; base += kCW * AM::UPW) {
         const int u0 = base + lane / LPR;
         const bool valid = u0 < rows;
         const int u = valid ? u0 : rows - 1;
@@ -491,7 +498,7 @@ template <class C>
 __device__ __forceinline__ void attn_backward_dkv(Ctx2& c, const LayerDev& W, int hc, int N, int NP, bool to_slot) {
     using AM = AttnMap<C>;
     constexpr int LPR = AM::LPR, DPL = AM::DPL;
-    constexpr int MR = C::kR / (kWarps * AM::UPW);          // rounds a warp can have
+    constexpr int MR = C::kR / (kCW * AM::UPW);          // rounds a warp can have
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane % LPR;
     const int rows = c.rows_act;
@@ -504,7 +511,7 @@ __device__ __forceinline__ void attn_backward_dkv(Ctx2& c, const LayerDev& W, in
     float dk[MR][DPL], dv[MR][DPL];
 #pragma unroll
     for (int rd = 0; rd < MR; ++rd) {
-        const int base = (warp + rd * kWarps) * AM::UPW;
+        const int base = (warp + rd * kCW) * AM::UPW;
 #pragma unroll
         for (int e = 0; e < DPL; ++e) { dk[rd][e] = 0.f; dv[rd][e] = 0.f; }
         if (base < rows) {
@@ -536,7 +543,7 @@ __device__ __forceinline__ void attn_backward_dkv(Ctx2& c, const LayerDev& W, in
         c.slot_acquire();
 #pragma unroll
         for (int rd = 0; rd < MR; ++rd) {
-            const int u0 = (warp + rd * kWarps) * AM::UPW + lane / LPR;
+            const int u0 = (warp + rd * kCW) * AM::UPW + lane / LPR;
             if (u0 < rows) can_store_group<DPL>(c.slot_hi, c.slot_lo, u0, sub, dk[rd]);
         }
         c.slot_post();
@@ -544,7 +551,7 @@ __device__ __forceinline__ void attn_backward_dkv(Ctx2& c, const LayerDev& W, in
     // dx_u += A_h^T (dk'_u + dv'_u - do_u): runs while the tensor core consumes d k'
 #pragma unroll
     for (int rd = 0; rd < MR; ++rd) {
-        const int base = (warp + rd * kWarps) * AM::UPW;
+        const int base = (warp + rd * kCW) * AM::UPW;
         if (base < rows) {
             const int u0 = base + lane / LPR;
             const int u = min(u0, rows - 1);
@@ -562,7 +569,7 @@ __device__ __forceinline__ void attn_backward_dkv(Ctx2& c, const LayerDev& W, in
         c.slot_acquire();
 #pragma unroll
         for (int rd = 0; rd < MR; ++rd) {
-            const int u0 = (warp + rd * kWarps) * AM::UPW + lane / LPR;
+            const int u0 = (warp + rd * kCW) * AM::UPW + lane / LPR;
             if (u0 < rows) can_store_group<DPL>(c.slot_hi, c.slot_lo, u0, sub, dv[rd]);
         }
         c.slot_post();
@@ -583,7 +590,7 @@ __device__ void forward_pass_tc(const ModelDev& M, Ctx2& c, float t_norm) {
     const int rows = c.rows_act;
 
     // layer-0 node stream: W_n [onehot_i, t] + b_n   (graph_transformer.py:99-103)
-    for (int idx = tid; idx < rows * C::kHP; idx += kThreads) {
+    for (int idx = tid; idx < rows * C::kHP; idx += kCT) {
         const int r = idx / C::kHP, d = idx - r * C::kHP;
         c.sN[r * C::LDH + d] = __ldg(M.emb + (r % N) * H + d) + t_norm * __ldg(M.embt + d);
     }
@@ -657,11 +664,11 @@ __device__ void forward_pass_tc(const ModelDev& M, Ctx2& c, float t_norm) {
         csync();
         c.mark(9);
         for (int ch = 0; ch < 4; ++ch) {
-            constexpr int MG = (R * 16) / kThreads;       // granules (row, 4 columns) per thread
+            constexpr int MG = (R * 16) / kCT;       // granules (row, 4 columns) per thread
             float4 gq[MG];
 #pragma unroll
             for (int g = 0; g < MG; ++g) {
-                const int idx = tid + g * kThreads;
+                const int idx = tid + g * kCT;
                 if (idx < rows * 16) {
                     const int r = idx >> 4, k4 = idx & 15;
                     const float4 v = *reinterpret_cast<const float4*>(sH + r * kLDF + ch * 64 + k4 * 4);
@@ -674,7 +681,7 @@ __device__ void forward_pass_tc(const ModelDev& M, Ctx2& c, float t_norm) {
             c.slot_acquire();
 #pragma unroll
             for (int g = 0; g < MG; ++g) {
-                const int idx = tid + g * kThreads;
+                const int idx = tid + g * kCT;
                 if (idx < rows * 16) can_store4(c.slot_hi, c.slot_lo, idx >> 4, idx & 15, gq[g]);
             }
             c.slot_post();
@@ -710,11 +717,11 @@ __device__ void backward_pass_tc(const ModelDev& M, Ctx2& c) {
     const int N = M.N, NP = M.NP, H = M.H;
     const int rows = c.rows_act;
 
-    for (int idx = tid; idx < rows * C::kHP; idx += kThreads) {
+    for (int idx = tid; idx < rows * C::kHP; idx += kCT) {
         const int r = idx / C::kHP, d = idx - r * C::kHP;
         c.sN[r * C::LDH + d] = __ldg(M.dec_w + d);               // dE_r/dn_r = w_dec  (node_decoder, :106)
     }
-    for (int idx = tid; idx < R * 4; idx += kThreads) c.sDX[idx] = 0.f;
+    for (int idx = tid; idx < R * 4; idx += kCT) c.sDX[idx] = 0.f;
     csync();
 
     for (int l = M.L - 1; l >= 0; --l) {
@@ -739,11 +746,11 @@ __device__ void backward_pass_tc(const ModelDev& M, Ctx2& c) {
         csync();
         c.mark(12);
         for (int ch = 0; ch < 4; ++ch) {
-            constexpr int MG = (R * 16) / kThreads;
+            constexpr int MG = (R * 16) / kCT;
             float4 gq[MG];
 #pragma unroll
             for (int g = 0; g < MG; ++g) {
-                const int idx = tid + g * kThreads;
+                const int idx = tid + g * kCT;
                 if (idx < rows * 16) {
                     const int r = idx >> 4, k4 = idx & 15;
                     const float4 p = *reinterpret_cast<const float4*>(st + M.off[ST_H1] + (size_t)r * (4 * H) + ch * 64 + k4 * 4);
@@ -754,7 +761,7 @@ __device__ void backward_pass_tc(const ModelDev& M, Ctx2& c) {
             c.slot_acquire();
 #pragma unroll
             for (int g = 0; g < MG; ++g) {
-                const int idx = tid + g * kThreads;
+                const int idx = tid + g * kCT;
                 if (idx < rows * 16) can_store4(c.slot_hi, c.slot_lo, idx >> 4, idx & 15, gq[g]);
             }
             c.slot_post();
@@ -779,12 +786,12 @@ __device__ void backward_pass_tc(const ModelDev& M, Ctx2& c) {
             // start reloading q | k' | v' and p of this chunk; the copies land while d o is read back
             {
                 const float* src = st + M.off[ST_QKV] + (size_t)hc * R * 3 * C::CWQ;
-                for (int idx = tid; idx < rows * 48; idx += kThreads) {
+                for (int idx = tid; idx < rows * 48; idx += kCT) {
                     const int r = idx / 48, c4 = idx - r * 48;
                     cp_async16(c.sQKV + r * C::LDQ + c4 * 4, src + (size_t)r * 192 + c4 * 4);
                 }
                 const float* srcp = st + M.off[ST_P] + (size_t)hc * R * NP;
-                for (int idx = tid; idx < (rows * NP) / 4; idx += kThreads) cp_async16(c.sP + idx * 4, srcp + idx * 4);
+                for (int idx = tid; idx < (rows * NP) / 4; idx += kCT) cp_async16(c.sP + idx * 4, srcp + idx * 4);
             }
             {   // d o_chunk = d att x Wo_b[l][hc]: TMEM -> shared
                 c.mark(15);
@@ -865,7 +872,7 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
         // ===================================================== TMA producer: streams the weight slices of every job
         if ((tid & 31) == 0) {
             uint32_t slice_i = 0;
-            long long pw[1] = {0};
+            long long pw[1] = {0}; (void)pw;
             for (uint32_t rep = 0; rep < reps; ++rep)
                 for (int j = 0; j < njobs; ++j) {
                     const TcJob jb = jobs[j];
@@ -883,59 +890,85 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
 #endif
         }
     } else if (warp == kComputeThreads / 32 + 1) {
-        // ===================================================== MMA issuer: walks the job table, one thread
-        if ((tid & 31) == 0) {
+        // ===================================================== MMA issuer: walks the job table.
+        // The whole warp runs the (warp-uniform) control flow and descriptor arithmetic, so that the operands of
+        // tcgen05.mma stay in uniform registers; one elected lane issues the MMAs and commits.
+        {
             uint32_t slice_i = 0, post_seq = 0, dq_idx = 0;
             long long iw[4] = {0, 0, 0, 0};
             const long long t_begin = clock64();
-            const float* nhat_hi = smem + C::oNhatHi; const float* nhat_lo = smem + C::oNhatLo;
-            const float* slot_hi = smem + C::oSlotHi; const float* slot_lo = smem + C::oSlotLo;
+            const uint32_t lane_id = tid & 31;
+            const uint32_t nhat_hi_a = smem_u32(smem + C::oNhatHi), nhat_lo_a = smem_u32(smem + C::oNhatLo);
+            const uint32_t slot_hi_a = smem_u32(smem + C::oSlotHi), slot_lo_a = smem_u32(smem + C::oSlotLo);
+            const uint32_t ring_a = smem_u32(smem + C::oW);
+            constexpr uint64_t kDescHi = ((uint64_t)(128u >> 4) << 32) | ((uint64_t)1 << 46);      // SBO = 128 B, version 1
+            constexpr uint64_t kDescA = kDescHi | ((uint64_t)((kCS * 4) >> 4) << 16);             // LBO = chunk stride
+            constexpr uint32_t a_step = (uint32_t)(2 * kCS * 4) >> 4;                             // two 16-byte k-chunks per MMA
             for (uint32_t rep = 0; rep < reps; ++rep)
                 for (int j = 0; j < njobs; ++j) {
-                    const TcJob jb = jobs[j];
-                    if (jb.wait_post) {
+                    // job fields, made warp-uniform
+                    const uint32_t* jw = reinterpret_cast<const uint32_t*>(jobs + j);      // words 3..6 of the 32-byte entry
+                    const uint32_t f0 = __shfl_sync(0xffffffffu, jw[3], 0), f1 = __shfl_sync(0xffffffffu, jw[4], 0);
+                    const uint32_t f2 = __shfl_sync(0xffffffffu, jw[5], 0), f3 = __shfl_sync(0xffffffffu, jw[6], 0);
+                    const uint32_t n_slices = f0 & 0xffffu, ks = f0 >> 16, n = f1 & 0xffffu;
+                    uint32_t dcol = f1 >> 16;
+                    const uint32_t a_slot = f2 & 0xffu, acc_first = (f2 >> 8) & 0xffu, wait_post = (f2 >> 16) & 0xffu, dbuf = f2 >> 24;
+                    const uint32_t commit_acc = f3 & 0xffu, commit_d1 = (f3 >> 8) & 0xffu;
+                    if (wait_post) {
                         ++post_seq;
                         TCP_BEGIN(); spin_until(ctr, post_seq, 7); TCP_END(iw, 0);
                     }
-                    uint32_t dcol = jb.d_col;
-                    if (jb.dbuf) {
+                    if (dbuf) {
                         TCP_BEGIN(); if (dq_idx >= 2) spin_until(ctr + 1, dq_idx - 1, 8); TCP_END(iw, 1);
-                        dcol += (dq_idx & 1u) * jb.n;
+                        dcol += (dq_idx & 1u) * n;
                     }
                     tc::fence_after_sync();
-                    const float* ahi = jb.a_slot ? slot_hi : nhat_hi;
-                    const float* alo = jb.a_slot ? slot_lo : nhat_lo;
-                    const uint32_t idesc = tc::idesc_tf32(64, jb.n);
+                    uint64_t dah = kDescA | (uint64_t)(((a_slot ? slot_hi_a : nhat_hi_a) >> 4) & 0x3FFFu);
+                    uint64_t dal = kDescA | (uint64_t)(((a_slot ? slot_lo_a : nhat_lo_a) >> 4) & 0x3FFFu);
+                    const uint32_t idesc = tc::idesc_tf32(64, (int)n);
                     const uint32_t d_tmem = tmem + dcol;
-                    const uint32_t blbo = (uint32_t)jb.n * 16u;
-                    uint32_t acc = jb.acc_first;
-                    for (uint32_t s = 0; s < jb.n_slices; ++s, ++slice_i) {
+                    const uint64_t descB = kDescHi | ((uint64_t)n << 16);                          // LBO = n * 16 B
+                    const uint32_t b_step = 2u * n;                                               // (2 * n * 16 B) >> 4
+                    const uint32_t lo_off = (ks * n * 4u) >> 4;                                   // lo image follows the hi image
+                    const uint32_t ksteps = ks >> 3;
+                    uint32_t acc = acc_first;
+                    for (uint32_t s = 0; s < n_slices; ++s, ++slice_i) {
                         const uint32_t stg = slice_i % kTcStages, use = slice_i / kTcStages;
+                        uint64_t dbh = descB | (uint64_t)(((ring_a + stg * (kTcStageFloats * 4)) >> 4) & 0x3FFFu);
+                        uint64_t dbl = dbh + lo_off;
                         { TCP_BEGIN(); mbar_wait_wd(bars + B_FULL + stg, use & 1u, 6); TCP_END(iw, 2); }
                         tc::fence_after_sync();
-                        const float* bhi = smem + C::oW + stg * kTcStageFloats;
-                        const float* blo = bhi + (uint32_t)jb.ks * jb.n;
-                        for (uint32_t kk = 0; kk < jb.ks; kk += 8) {
-                            const uint32_t ca = (s * jb.ks + kk) >> 2, cb = kk >> 2;
-                            const uint64_t dah = tc::smem_desc(ahi + ca * kCS, kCS * 4, 128), dal = tc::smem_desc(alo + ca * kCS, kCS * 4, 128);
-                            const uint64_t dbh = tc::smem_desc(bhi + cb * jb.n * 4, blbo, 128), dbl = tc::smem_desc(blo + cb * jb.n * 4, blbo, 128);
-                            tc::mma_tf32_ss(d_tmem, dal, dbh, idesc, acc);
-                            tc::mma_tf32_ss(d_tmem, dah, dbl, idesc, 1u);
-                            tc::mma_tf32_ss(d_tmem, dah, dbh, idesc, 1u);
-                            acc = 1u;
+                        if (tc::elect_one()) {
+                            tc::mma_tf32_ss(d_tmem, dal, dbh, idesc, acc);          // first k-step of the slice (may overwrite D)
+                            tc::mma_tf32_acc(d_tmem, dah, dbl, idesc);
+                            tc::mma_tf32_acc(d_tmem, dah, dbh, idesc);
                         }
-                        tc::commit(bars + B_EMPTY + stg);
+                        acc = 1u;
+                        for (uint32_t kk = 1; kk < ksteps; ++kk) {
+                            dah += a_step; dal += a_step; dbh += b_step; dbl += b_step;
+                            if (tc::elect_one()) {
+                                tc::mma_tf32_acc(d_tmem, dal, dbh, idesc);
+                                tc::mma_tf32_acc(d_tmem, dah, dbl, idesc);
+                                tc::mma_tf32_acc(d_tmem, dah, dbh, idesc);
+                            }
+                        }
+                        dah += a_step; dal += a_step;
+                        if (tc::elect_one()) tc::commit(bars + B_EMPTY + stg);
                     }
-                    if (jb.a_slot) tc::commit(bars + B_SLOT);
-                    if (jb.dbuf) { tc::commit(bars + B_DQ + (dq_idx & 1u)); ++dq_idx; }
-                    if (jb.commit_acc) tc::commit(bars + B_ACC);
-                    if (jb.commit_d1) tc::commit(bars + B_D1);
+                    if (tc::elect_one()) {
+                        if (a_slot) tc::commit(bars + B_SLOT);
+                        if (dbuf) tc::commit(bars + B_DQ + (dq_idx & 1u));
+                        if (commit_acc) tc::commit(bars + B_ACC);
+                        if (commit_d1) tc::commit(bars + B_D1);
+                    }
+                    if (dbuf) ++dq_idx;
+                    __syncwarp();
                 }
 #ifdef DFF_TC_PROFILE
-            if (T.dbg) { T.dbg[blockIdx.x * 16 + 9] = iw[0]; T.dbg[blockIdx.x * 16 + 10] = iw[1]; T.dbg[blockIdx.x * 16 + 11] = iw[2];
+            if (T.dbg && lane_id == 0) { T.dbg[blockIdx.x * 16 + 9] = iw[0]; T.dbg[blockIdx.x * 16 + 10] = iw[1]; T.dbg[blockIdx.x * 16 + 11] = iw[2];
                          T.dbg[blockIdx.x * 16 + 12] = clock64() - t_begin; }
 #else
-            (void)iw; (void)t_begin;
+            (void)iw; (void)t_begin; (void)lane_id;
 #endif
         }
     } else {
@@ -960,7 +993,7 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
             const int s0 = g * M.S;
             c.S_act = min(M.S, A.B - s0);
             c.rows_act = c.S_act * N;
-            for (int idx = tid; idx < R * 3; idx += kThreads) {
+            for (int idx = tid; idx < R * 3; idx += kCT) {
                 const int r = idx / 3, cc = idx - r * 3;
                 const bool ok = r < c.rows_act;
                 c.sX[r * 4 + cc] = ok ? A.x[((size_t)s0 * N + r) * 3 + cc] : 0.f;
@@ -986,7 +1019,7 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
                 forward_pass_tc<C>(M, c, t_norm);
                 if (A.energy_out != nullptr) {   // node_decoder (graph_transformer.py:106)
                     const int lane = tid & 31;
-                    for (int r = warp; r < c.rows_act; r += kWarps) {
+                    for (int r = warp; r < c.rows_act; r += kCW) {
                         float s = 0.f;
                         for (int d = lane; d < M.H; d += 32) s += c.sN[r * C::LDH + d] * __ldg(M.dec_w + d);
                         s = warp_sum(s);
@@ -999,7 +1032,7 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
 
                 if (A.mode == MODE_SCORE) {
                     if (A.eps_out != nullptr)
-                        for (int idx = tid; idx < c.rows_act * 3; idx += kThreads) {
+                        for (int idx = tid; idx < c.rows_act * 3; idx += kCT) {
                             const int r = idx / 3, cc = idx - r * 3;
                             A.eps_out[((size_t)s0 * N + r) * 3 + cc] = -c.sDX[r * 4 + cc];
                         }
@@ -1047,7 +1080,7 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
                     }
                 } else {
                     // ForcesWrapper (dynamics/langevin.py:78-87) + _langevin_timestep / _overdamped_timestep
-                    for (int idx = tid; idx < c.rows_act * 3; idx += kThreads) {
+                    for (int idx = tid; idx < c.rows_act * 3; idx += kCT) {
                         const int r = idx / 3, cc = idx - r * 3;
                         const int o = r * 4 + cc;
                         const size_t ge = ((size_t)s0 * N + r) * 3 + cc;
@@ -1076,7 +1109,7 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
                         csync();
                         const int f = step / A.save_interval;
                         if (A.frames != nullptr)
-                            for (int idx = tid; idx < c.rows_act * 3; idx += kThreads) {
+                            for (int idx = tid; idx < c.rows_act * 3; idx += kCT) {
                                 const int r = idx / 3, cc = idx - r * 3;
                                 A.frames[((size_t)f * A.B + s0) * N * 3 + (size_t)r * 3 + cc] = c.sX[r * 4 + cc];
                             }
@@ -1093,7 +1126,7 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
                 csync();
             }
             if (A.mode != MODE_SCORE) {
-                for (int idx = tid; idx < c.rows_act * 3; idx += kThreads) {
+                for (int idx = tid; idx < c.rows_act * 3; idx += kCT) {
                     const int r = idx / 3, cc = idx - r * 3;
                     A.x[((size_t)s0 * N + r) * 3 + cc] = c.sX[r * 4 + cc];
                     if (A.v != nullptr) A.v[((size_t)s0 * N + r) * 3 + cc] = c.sV[r * 4 + cc];
