@@ -322,16 +322,18 @@ def main():
             traffic = json.load(open(ps)).get(a.workload, {}).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
+    cfg_used = eng.last_config
+    kernel = "dff_fused_tc_kernel (tcgen05.mma kind::tf32, TMEM accumulators)" if cfg_used == "tc" else f"dff_fused_kernel ({cfg_used}; mma.sync tf32)"
     out = {"metric": metric, "value": value, "unit": unit, "md_steps_per_s": value / (world * B), "n_gpus": world, "steps": a.steps,
            "warmup": max(a.warmup, 3), "ms_per_step": dev_ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": f"synthetic coordinates (noised folded structure); {wdesc}", "config": config,
            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "finite": finite, "wall_s_timed_region": t_wall,
            "roofline": {"bound": "tensor", "achieved": achieved, "peak": bf16 / passes, "unit": "TFLOP/s", "frac": achieved / (bf16 / passes),
-                        "traffic": traffic, "kernel": "dff_fused_kernel", "flops_per_launch": eng.flops_per_sample * B * per_step,
+                        "traffic": traffic, "kernel": kernel, "flops_per_launch": eng.flops_per_sample * B * per_step,
                         "note": f"collapsed-formulation FLOPs (SURVEY 8d) per launch / CUDA-event time; peak = {pk_src} / {passes} passes "
-                                "(fp32-grade split precision). This round's kernel runs the contractions as fp32 FFMA on CUDA cores "
-                                "(no tensor-core passes yet), so frac is also a fraction of a peak it cannot reach: "
-                                "fp32 SIMT peak is ~72 TFLOP/s."}}
+                                "(fp32-grade 3x split precision). The tcgen05 kernel issues kind::tf32 MMAs (half the bf16 rate) on 64-row "
+                                "tiles (half the M=128 rate), so its own ceiling is a quarter of this peak; for this workload "
+                                "(20 node rows per CTA) the honest bound is latency, not the tensor pipe (DESIGN.md section 7)."}}
     if world == 1 and not a.no_cpu_baseline:
         done, el, threads = cpu_port_rate(w, seconds=15.0, max_steps=40, warm=2)
         out["cpu_baseline"] = {"value": done * B / el, "unit": unit, "cores": threads, "kind": "port",

@@ -88,6 +88,9 @@ int dff_model_layers(const dff_model_t* m);
 int dff_model_device(const dff_model_t* m);
 /* Kernel-launch counter of this handle (bench.py reports it as gpu_launches). */
 int64_t dff_model_launch_count(const dff_model_t* m);
+/* Launch configuration the last call of this handle used: "tc" (tcgen05/TMEM kernel, csrc/dff_kernel_tc.cuh) or
+ * "wide" / "tall" / "duo" (mma.sync kernel, csrc/dff_kernel.cuh); "none" before the first launch. */
+const char* dff_model_last_config(const dff_model_t* m);
 /* Algorithmic FLOPs of one force evaluation for one sample in the collapsed formulation the
  * kernel executes (fwd + backward w.r.t. x). */
 double dff_model_flops_per_sample(const dff_model_t* m);

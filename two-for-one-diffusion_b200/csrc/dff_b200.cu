@@ -66,6 +66,7 @@ struct dff_model {
     uint32_t* d_flags = nullptr;
     float* d_sched = nullptr;  size_t d_sched_T = 0;
     int last_R = 0, last_S = 0;
+    const char* last_cfg = "none";
     // tcgen05 configuration (hidden = 64): job table + canonical hi/lo weight panels
     bool tc_ok = false;
     v2::TcJob* d_jobs = nullptr;
@@ -147,12 +148,13 @@ int launch_tc(dff_model* m, const ModelDev& M, const StepArgs& A, int grid, cuda
     return DFF_OK;
 }
 
-// Launch policy.  Three configurations of the same kernel:
-//   wide : R = 64 rows, 1 head per chunk, 4-stage ring, 1 CTA/SM   (anything; the only one for N > 32)
-//   tall : R = 32 rows, 2 heads per chunk, 4-stage ring, 1 CTA/SM  (small batches: fewer, fatter phases)
-//   duo  : R = 32 rows, 1 head per chunk, 2-stage ring, <= 128 regs, 2 CTAs/SM (one CTA's tensor-core GEMMs overlap
-//          the other's CUDA-core phases)
-// DFF_CONFIG=wide|tall|duo overrides the choice (profiling).
+// Launch policy.  Four configurations:
+//   tc   : tcgen05 kernel (dff_kernel_tc.cuh): 64-row passes, TMEM accumulators, asynchronous MMA issue; hidden = 64 nets.
+//          The default wherever it applies (measured: C2 3179 vs 2270 steps/s tall, C3 350 vs 265 duo).
+//   wide : mma.sync kernel, R = 64 rows, 1 head per chunk, 4-stage ring, 1 CTA/SM   (anything; the only one for N > 32)
+//   tall : mma.sync kernel, R = 32 rows, 2 heads per chunk, 4-stage ring, 1 CTA/SM  (small batches: fewer, fatter phases)
+//   duo  : mma.sync kernel, R = 32 rows, 1 head per chunk, 2-stage ring, <= 128 regs, 2 CTAs/SM
+// DFF_CONFIG=tc|legacy|wide|tall|duo overrides the choice (profiling / A-B runs).
 int launch(dff_model* m, StepArgs& A, cudaStream_t stream) {
     if (A.B <= 0) return DFF_OK;
     if (A.B > m->max_batch) return fail(DFF_EINVAL, "batch %d exceeds max_batch %d given to dff_model_create", A.B, m->max_batch);
@@ -170,7 +172,10 @@ int launch(dff_model* m, StepArgs& A, cudaStream_t stream) {
     else if (need1 <= s32) cfg = TALL;
     else if (rows32_full && kThreads == 256) cfg = DUO;
     else cfg = WIDE;
+    const auto legacy = cfg;           // the mma.sync kernel's choice (DFF_CONFIG=legacy)
+    if (m->tc_ok) cfg = TC;
     if (const char* e = getenv("DFF_CONFIG")) {
+        if (!strcmp(e, "legacy")) cfg = legacy;
         if (!strcmp(e, "wide")) cfg = WIDE;
         else if (!strcmp(e, "tall") && s32 >= 1) cfg = TALL;
         else if (!strcmp(e, "duo") && s32 >= 1 && kThreads == 256) cfg = DUO;
@@ -186,7 +191,7 @@ int launch(dff_model* m, StepArgs& A, cudaStream_t stream) {
         if (grid > m->scratch_ctas) return fail(DFF_EINVAL, "internal: grid %d exceeds scratch slots %d", grid, m->scratch_ctas);
         const double slices = (double)((n_groups + grid - 1) / grid) * (double)A.n_steps * (double)m->tc.nslice_all;
         if (slices >= 4.0e9) return fail(DFF_EINVAL, "n_steps %d too large for one launch; split the call (e.g. per save interval)", A.n_steps);
-        m->last_R = 64; m->last_S = S;
+        m->last_R = 64; m->last_S = S; m->last_cfg = "tc";
         if (m->NP <= 12) return launch_tc<v2::TcCfg<12>>(m, M, A, grid, stream);
         return launch_tc<v2::TcCfg<32>>(m, M, A, grid, stream);
     }
@@ -207,7 +212,7 @@ int launch(dff_model* m, StepArgs& A, cudaStream_t stream) {
         const double slices = (double)((n_groups + grid - 1) / grid) * (double)A.n_steps * (double)(A.need_backward ? M.nslice_all : M.nslice_fwd);
         if (slices >= 4.0e9) return fail(DFF_EINVAL, "n_steps %d too large for one launch; split the call (e.g. per save interval)", A.n_steps);
     }
-    m->last_R = R; m->last_S = S;
+    m->last_R = R; m->last_S = S; m->last_cfg = cfg == WIDE ? "wide" : cfg == TALL ? "tall" : "duo";
     if (m->HP == 64) {
         if (cfg == WIDE) return launch_cfg<Cfg<64, 64, 1>, 1>(m, M, A, grid, stream);
         if (cfg == TALL) return launch_cfg<Cfg<64, 32, 2>, 1>(m, M, A, grid, stream);
@@ -535,6 +540,7 @@ int dff_model_hidden(const dff_model_t* m) { return m ? m->H : 0; }
 int dff_model_layers(const dff_model_t* m) { return m ? m->L : 0; }
 int dff_model_device(const dff_model_t* m) { return m ? m->device : -1; }
 int64_t dff_model_launch_count(const dff_model_t* m) { return m ? m->launches : 0; }
+const char* dff_model_last_config(const dff_model_t* m) { return m ? m->last_cfg : "none"; }
 
 double dff_model_flops_per_sample(const dff_model_t* m) {
     if (!m) return 0;

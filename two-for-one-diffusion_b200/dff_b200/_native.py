@@ -38,6 +38,7 @@ SYMBOLS = {
     "dff_model_layers": (C.c_int, [_vp]),
     "dff_model_device": (C.c_int, [_vp]),
     "dff_model_launch_count": (C.c_int64, [_vp]),
+    "dff_model_last_config": (C.c_char_p, [_vp]),
     "dff_model_flops_per_sample": (C.c_double, [_vp]),
     "dff_score_dev": (C.c_int, [_vp, _vp, C.c_float, C.c_int, _vp, _vp, _vp]),
     "dff_score_host": (C.c_int, [_vp, _vp, C.c_float, C.c_int, _vp, _vp]),

@@ -84,6 +84,11 @@ class ScoreEngine:
         return int(nat.lib().dff_model_launch_count(self._h))
 
     @property
+    def last_config(self) -> str:
+        """Launch configuration of the last call: "tc" (tcgen05/TMEM kernel) or "wide"/"tall"/"duo" (mma.sync kernel)."""
+        return nat.lib().dff_model_last_config(self._h).decode()
+
+    @property
     def flops_per_sample(self) -> float:
         return float(nat.lib().dff_model_flops_per_sample(self._h))
 
