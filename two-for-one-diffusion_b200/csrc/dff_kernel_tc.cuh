@@ -210,6 +210,7 @@ struct Ctx2 {
     uint32_t tmem;
     uint32_t n_post, n_drain, n_acc, n_d1, n_slot;   // identical in every compute thread
     bool slot_held;
+    bool pairs;            // pair-local attention routines (groups with more rows than lane groups)
     long long tw[8];       // DFF_TC_PROFILE: cycles waited on {dq, acc, d1, slot}
 #ifdef DFF_TC_PROFILE
     long long ph[32], last;
@@ -578,6 +579,240 @@ __device__ __forceinline__ void attn_backward_dkv(Ctx2& c, const LayerDev& W, in
     }
 }
 
+// ------------------------------------------------------------------ pair-local attention (large groups)
+// Same lane mapping as the row-local routines above, but a lane group owns TWO consecutive node rows of a sample: the
+// k' / v' / q / d o rows that both need are read from shared memory once.  The attention phases of a full 64-row
+// group are bound by the shared-memory pipe (every LDS.128 of a warp is four wavefronts), so this is ~1.5x faster
+// there; for small groups (rows <= lane groups) the row-local form has the shorter dependent chain and is kept.
+struct PairUnit { int r0, ia, ib; bool valid, has_b; };
+template <class C>
+__device__ __forceinline__ PairUnit pair_unit(int unit, int n_units, int pps, int N) {
+    PairUnit u;
+    u.valid = unit < n_units;
+    const int uc = u.valid ? unit : n_units - 1;
+    const int s = uc / pps, pi = uc - s * pps;
+    u.r0 = s * N; u.ia = 2 * pi; u.has_b = u.ia + 1 < N; u.ib = u.has_b ? u.ia + 1 : u.ia;
+    return u;
+}
+template <int LPR, int DPL>
+__device__ __forceinline__ void load_cols(float (&v)[DPL], const float* __restrict__ src) {
+    if (DPL == 4) {
+        const float4 t = *reinterpret_cast<const float4*>(src);
+        v[0] = t.x; v[1] = t.y; v[2 % DPL] = t.z; v[3 % DPL] = t.w;
+    } else {
+        const float2 t = *reinterpret_cast<const float2*>(src);
+        v[0] = t.x; v[1] = t.y;
+    }
+}
+// two 64-long dot products against the same (register-free) streamed row b: a0 . b, a1 . b
+__device__ __forceinline__ void dot64x2(const float* __restrict__ a0, const float* __restrict__ a1, const float* __restrict__ b,
+                                        float& r0, float& r1) {
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f, e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+        const float4 y = *reinterpret_cast<const float4*>(b + 4 * t);
+        const float4 x = *reinterpret_cast<const float4*>(a0 + 4 * t), z = *reinterpret_cast<const float4*>(a1 + 4 * t);
+        d0 = fmaf(x.x, y.x, d0); d1 = fmaf(x.y, y.y, d1); d2 = fmaf(x.z, y.z, d2); d3 = fmaf(x.w, y.w, d3);
+        e0 = fmaf(z.x, y.x, e0); e1 = fmaf(z.y, y.y, e1); e2 = fmaf(z.z, y.z, e2); e3 = fmaf(z.w, y.w, e3);
+    }
+    r0 = (d0 + d1) + (d2 + d3);
+    r1 = (e0 + e1) + (e2 + e3);
+}
+
+template <class C>
+__device__ __forceinline__ void attn_forward_pairs(Ctx2& c, const LayerDev& W, int hc, int N, int NP, float* st_p) {
+    using AM = AttnMap<C>;
+    constexpr int LPR = AM::LPR, DPL = AM::DPL, NG = kCW * AM::UPW;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane % LPR, gbase = lane - sub, gid = warp * AM::UPW + lane / LPR;
+    const int pps = (N + 1) >> 1, n_units = c.S_act * pps;
+    float cc[DPL], ax[DPL][3];
+#pragma unroll
+    for (int e = 0; e < DPL; ++e) {
+        const int col = hc * 64 + sub * DPL + e;
+        cc[e] = __ldg(W.cvec + col);
+        const float4 a4 = __ldg(reinterpret_cast<const float4*>(W.A + col * 4));
+        ax[e][0] = a4.x; ax[e][1] = a4.y; ax[e][2] = a4.z;
+    }
+    const bool act = sub < N;
+    for (int base = 0; base < n_units; base += NG) {
+        const PairUnit u = pair_unit<C>(base + gid, n_units, pps, N);
+        const int ra = u.r0 + u.ia, rb = u.r0 + u.ib;
+        float da, db;
+        dot64x2(c.sQKV + ra * C::LDQ, c.sQKV + rb * C::LDQ, c.sQKV + (u.r0 + min(sub, N - 1)) * C::LDQ + 64, da, db);
+        const float la = act ? kAttnScale * da : -INFINITY, lb = act ? kAttnScale * db : -INFINITY;
+        const float ma = group_max<LPR>(la), mb = group_max<LPR>(lb);
+        const float ea = act ? expf(la - ma) : 0.f, eb = act ? expf(lb - mb) : 0.f;
+        const float pa = ea / group_sum<LPR>(ea), pb = eb / group_sum<LPR>(eb);
+        if (u.valid && sub < NP) {
+            st_p[(size_t)ra * NP + sub] = pa;
+            if (u.has_b) st_p[(size_t)rb * NP + sub] = pb;
+        }
+        float oa[DPL], ob[DPL];
+#pragma unroll
+        for (int e = 0; e < DPL; ++e) { oa[e] = 0.f; ob[e] = 0.f; }
+        const float* vs = c.sQKV + u.r0 * C::LDQ + 128 + sub * DPL;
+        for (int j = 0; j < N; ++j) {
+            float v[DPL];
+            load_cols<LPR, DPL>(v, vs + j * C::LDQ);
+            const float wa = __shfl_sync(0xffffffffu, pa, gbase + j), wb = __shfl_sync(0xffffffffu, pb, gbase + j);
+#pragma unroll
+            for (int e = 0; e < DPL; ++e) { oa[e] = fmaf(wa, v[e], oa[e]); ob[e] = fmaf(wb, v[e], ob[e]); }
+        }
+        {
+            const float x0 = c.sX[ra * 4], x1 = c.sX[ra * 4 + 1], x2 = c.sX[ra * 4 + 2];
+            const float y0 = c.sX[rb * 4], y1 = c.sX[rb * 4 + 1], y2 = c.sX[rb * 4 + 2];
+#pragma unroll
+            for (int e = 0; e < DPL; ++e) {
+                oa[e] += cc[e] - (ax[e][0] * x0 + ax[e][1] * x1 + ax[e][2] * x2);
+                ob[e] += cc[e] - (ax[e][0] * y0 + ax[e][1] * y1 + ax[e][2] * y2);
+            }
+        }
+        c.slot_acquire();
+        if (u.valid) {
+            can_store_group<DPL>(c.slot_hi, c.slot_lo, ra, sub, oa);
+            if (u.has_b) can_store_group<DPL>(c.slot_hi, c.slot_lo, rb, sub, ob);
+        }
+    }
+}
+
+template <class C>
+__device__ __forceinline__ void attn_backward_ds_dq_pairs(Ctx2& c, int N, int NP, bool want_dq) {
+    using AM = AttnMap<C>;
+    constexpr int LPR = AM::LPR, DPL = AM::DPL, NG = kCW * AM::UPW;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane % LPR, gbase = lane - sub, gid = warp * AM::UPW + lane / LPR;
+    const int pps = (N + 1) >> 1, n_units = c.S_act * pps;
+    const bool act = sub < N;
+    for (int base = 0; base < n_units; base += NG) {
+        const PairUnit u = pair_unit<C>(base + gid, n_units, pps, N);
+        const int ra = u.r0 + u.ia, rb = u.r0 + u.ib;
+        float dpa, dpb;
+        dot64x2(c.sO + ra * C::LDO, c.sO + rb * C::LDO, c.sQKV + (u.r0 + min(sub, N - 1)) * C::LDQ + 128, dpa, dpb);
+        const float pa = act ? c.sP[ra * NP + sub] : 0.f, pb = act ? c.sP[rb * NP + sub] : 0.f;
+        const float dsa = pa * (dpa - group_sum<LPR>(pa * dpa)), dsb = pb * (dpb - group_sum<LPR>(pb * dpb));
+        if (u.valid && sub < NP) {
+            c.sDS[ra * NP + sub] = dsa;
+            if (u.has_b) c.sDS[rb * NP + sub] = dsb;
+        }
+        if (want_dq) {
+            float qa[DPL], qb[DPL];
+#pragma unroll
+            for (int e = 0; e < DPL; ++e) { qa[e] = 0.f; qb[e] = 0.f; }
+            const float* ks = c.sQKV + u.r0 * C::LDQ + 64 + sub * DPL;
+            for (int j = 0; j < N; ++j) {
+                float v[DPL];
+                load_cols<LPR, DPL>(v, ks + j * C::LDQ);
+                const float wa = __shfl_sync(0xffffffffu, dsa, gbase + j), wb = __shfl_sync(0xffffffffu, dsb, gbase + j);
+#pragma unroll
+                for (int e = 0; e < DPL; ++e) { qa[e] = fmaf(wa, v[e], qa[e]); qb[e] = fmaf(wb, v[e], qb[e]); }
+            }
+#pragma unroll
+            for (int e = 0; e < DPL; ++e) { qa[e] *= kAttnScale; qb[e] *= kAttnScale; }
+            c.slot_acquire();
+            if (u.valid) {
+                can_store_group<DPL>(c.slot_hi, c.slot_lo, ra, sub, qa);
+                if (u.has_b) can_store_group<DPL>(c.slot_hi, c.slot_lo, rb, sub, qb);
+            }
+        }
+    }
+}
+
+template <class C>
+__device__ __forceinline__ void attn_backward_dkv_pairs(Ctx2& c, const LayerDev& W, int hc, int N, int NP, bool to_slot) {
+    using AM = AttnMap<C>;
+    constexpr int LPR = AM::LPR, DPL = AM::DPL, NG = kCW * AM::UPW;
+    constexpr int MR = 2;                                    // rounds: pairs per CTA <= 2 * lane groups (checked by the host)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane % LPR, gid = warp * AM::UPW + lane / LPR;
+    const int pps = (N + 1) >> 1, n_units = c.S_act * pps;
+    float ax[DPL][3];
+#pragma unroll
+    for (int e = 0; e < DPL; ++e) {
+        const float4 a4 = __ldg(reinterpret_cast<const float4*>(W.A + (hc * 64 + sub * DPL + e) * 4));
+        ax[e][0] = a4.x; ax[e][1] = a4.y; ax[e][2] = a4.z;
+    }
+    float dk[MR][2][DPL], dv[MR][2][DPL];
+#pragma unroll
+    for (int rd = 0; rd < MR; ++rd) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int e = 0; e < DPL; ++e) { dk[rd][h][e] = 0.f; dv[rd][h][e] = 0.f; }
+        if (rd * NG < n_units) {
+            const PairUnit u = pair_unit<C>(rd * NG + gid, n_units, pps, N);
+            // key rows ja = u.ia, jb = u.ib of the sample; the weights of both sit next to each other (ia is even)
+            const float* wk = c.sDS + u.r0 * NP + u.ia;
+            const float* wv = c.sP + u.r0 * NP + u.ia;
+            const float* qs = c.sQKV + u.r0 * C::LDQ + sub * DPL;
+            const float* os = c.sO + u.r0 * C::LDO + sub * DPL;
+            for (int i = 0; i < N; ++i) {
+                const float2 a = *reinterpret_cast<const float2*>(wk + i * NP), b = *reinterpret_cast<const float2*>(wv + i * NP);
+                float q[DPL], o[DPL];
+                load_cols<LPR, DPL>(q, qs + i * C::LDQ);
+                load_cols<LPR, DPL>(o, os + i * C::LDO);
+#pragma unroll
+                for (int e = 0; e < DPL; ++e) {
+                    dk[rd][0][e] = fmaf(a.x, q[e], dk[rd][0][e]); dk[rd][1][e] = fmaf(a.y, q[e], dk[rd][1][e]);
+                    dv[rd][0][e] = fmaf(b.x, o[e], dv[rd][0][e]); dv[rd][1][e] = fmaf(b.y, o[e], dv[rd][1][e]);
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int e = 0; e < DPL; ++e) dk[rd][h][e] *= kAttnScale;
+        }
+    }
+    if (to_slot) {          // job d k'
+        c.slot_acquire();
+#pragma unroll
+        for (int rd = 0; rd < MR; ++rd)
+            if (rd * NG + gid < n_units) {
+                const PairUnit u = pair_unit<C>(rd * NG + gid, n_units, pps, N);
+                can_store_group<DPL>(c.slot_hi, c.slot_lo, u.r0 + u.ia, sub, dk[rd][0]);
+                if (u.has_b) can_store_group<DPL>(c.slot_hi, c.slot_lo, u.r0 + u.ib, sub, dk[rd][1]);
+            }
+        c.slot_post();
+    }
+    // dx_j += A_h^T (dk'_j + dv'_j - do_j): runs while the tensor core consumes d k'
+#pragma unroll
+    for (int rd = 0; rd < MR; ++rd)
+        if (rd * NG < n_units) {
+            const PairUnit u = pair_unit<C>(rd * NG + gid, n_units, pps, N);
+            float g[2][3];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int row = u.r0 + (h ? u.ib : u.ia);
+                g[h][0] = g[h][1] = g[h][2] = 0.f;
+#pragma unroll
+                for (int e = 0; e < DPL; ++e) {
+                    const float t = dk[rd][h][e] + dv[rd][h][e] - c.sO[row * C::LDO + sub * DPL + e];
+                    g[h][0] = fmaf(ax[e][0], t, g[h][0]); g[h][1] = fmaf(ax[e][1], t, g[h][1]); g[h][2] = fmaf(ax[e][2], t, g[h][2]);
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) { g[h][0] = group_sum<LPR>(g[h][0]); g[h][1] = group_sum<LPR>(g[h][1]); g[h][2] = group_sum<LPR>(g[h][2]); }
+            if (u.valid && sub == 0) {
+                const int ra = u.r0 + u.ia, rb = u.r0 + u.ib;
+                c.sDX[ra * 4] += g[0][0]; c.sDX[ra * 4 + 1] += g[0][1]; c.sDX[ra * 4 + 2] += g[0][2];
+                if (u.has_b) { c.sDX[rb * 4] += g[1][0]; c.sDX[rb * 4 + 1] += g[1][1]; c.sDX[rb * 4 + 2] += g[1][2]; }
+            }
+        }
+    if (to_slot) {          // job d v'
+        c.slot_acquire();
+#pragma unroll
+        for (int rd = 0; rd < MR; ++rd)
+            if (rd * NG + gid < n_units) {
+                const PairUnit u = pair_unit<C>(rd * NG + gid, n_units, pps, N);
+                can_store_group<DPL>(c.slot_hi, c.slot_lo, u.r0 + u.ia, sub, dv[rd][0]);
+                if (u.has_b) can_store_group<DPL>(c.slot_hi, c.slot_lo, u.r0 + u.ib, sub, dv[rd][1]);
+            }
+        c.slot_post();
+    } else {
+        csync();
+    }
+}
+
 // FF hidden block [rows][4H] TMEM -> shared (row stride LDF), so that the GELU phases can be spread over all threads
 constexpr int kLDF = 256 + 4;
 
@@ -627,7 +862,8 @@ __device__ void forward_pass_tc(const ModelDev& M, Ctx2& c, float t_norm) {
                 c.mark(2);
             }
             // logits, softmax, P V' - A x_i + c -> canonical operand of the out-projection (row-local, no barrier inside)
-            attn_forward_rows<C>(c, W, hc, N, NP, st + M.off[ST_P] + (size_t)hc * R * NP);
+            if (c.pairs) attn_forward_pairs<C>(c, W, hc, N, NP, st + M.off[ST_P] + (size_t)hc * R * NP);
+            else attn_forward_rows<C>(c, W, hc, N, NP, st + M.off[ST_P] + (size_t)hc * R * NP);
             c.mark(3);
             c.slot_post();
             c.mark(4);
@@ -806,11 +1042,13 @@ __device__ void backward_pass_tc(const ModelDev& M, Ctx2& c) {
                 c.dq_release();
                 c.mark(16);
             }
-            attn_backward_ds_dq<C>(c, N, NP, l > 0);
+            if (c.pairs) attn_backward_ds_dq_pairs<C>(c, N, NP, l > 0);
+            else attn_backward_ds_dq<C>(c, N, NP, l > 0);
             c.mark(17);
             if (l > 0) c.slot_post(); else csync();          // every ds of the sample is in sDS before the key-row passes
             c.mark(18);
-            attn_backward_dkv<C>(c, W, hc, N, NP, l > 0);
+            if (c.pairs) attn_backward_dkv_pairs<C>(c, W, hc, N, NP, l > 0);
+            else attn_backward_dkv<C>(c, W, hc, N, NP, l > 0);
             c.mark(19);
         }
         if (l > 0) {
@@ -993,6 +1231,7 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
             const int s0 = g * M.S;
             c.S_act = min(M.S, A.B - s0);
             c.rows_act = c.S_act * N;
+            c.pairs = c.rows_act > kCW * AttnMap<C>::UPW;
             for (int idx = tid; idx < R * 3; idx += kCT) {
                 const int r = idx / 3, cc = idx - r * 3;
                 const bool ok = r < c.rows_act;
