@@ -399,6 +399,59 @@ __device__ __forceinline__ float dot64(const float* __restrict__ a, const float*
     }
     return (d0 + d1) + (d2 + d3);
 }
+// dots of one (or two) shared-memory rows a (a2) with the N rows b_j of the sample, for all j at once:
+// every lane takes the DPL columns it owns, forms the partial products for every key j and the partials are then
+// summed across the group by a transpose-reduce (LPR - 1 shuffles), after which lane j holds  a . b_j.
+// Compared with "lane j walks the whole rows a and b_j" this moves 1 + N instead of 32 LDS.128 per lane through the
+// shared-memory pipe, which is what bounds the attention phases.
+template <int LPR>
+__device__ __forceinline__ float transpose_reduce(float (&v)[LPR], int sub) {
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) {
+        const bool up = (sub & o) != 0;
+#pragma unroll
+        for (int k = 0; k < o; ++k) {
+            const float keep = up ? v[k + o] : v[k];
+            const float send = up ? v[k] : v[k + o];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+    return v[0];
+}
+template <int LPR, int DPL, bool TWO>
+__device__ __forceinline__ void group_dots(const float* __restrict__ a, const float* __restrict__ a2, const float* __restrict__ b, int ld,
+                                           int N, int sub, float& r, float& r2) {
+    float av[DPL], av2[DPL];
+    if (DPL == 4) {
+        const float4 t = *reinterpret_cast<const float4*>(a + sub * DPL);
+        av[0] = t.x; av[1] = t.y; av[2 % DPL] = t.z; av[3 % DPL] = t.w;
+        if (TWO) { const float4 u = *reinterpret_cast<const float4*>(a2 + sub * DPL); av2[0] = u.x; av2[1] = u.y; av2[2 % DPL] = u.z; av2[3 % DPL] = u.w; }
+    } else {
+        const float2 t = *reinterpret_cast<const float2*>(a + sub * DPL);
+        av[0] = t.x; av[1] = t.y;
+        if (TWO) { const float2 u = *reinterpret_cast<const float2*>(a2 + sub * DPL); av2[0] = u.x; av2[1] = u.y; }
+    }
+    float part[LPR], part2[TWO ? LPR : 1];
+#pragma unroll
+    for (int j = 0; j < LPR; ++j) {
+        float s = 0.f, s2 = 0.f;
+        if (j < N) {
+            if (DPL == 4) {
+                const float4 y = *reinterpret_cast<const float4*>(b + j * ld + sub * DPL);
+                s = fmaf(av[0], y.x, fmaf(av[1], y.y, fmaf(av[2 % DPL], y.z, av[3 % DPL] * y.w)));
+                if (TWO) s2 = fmaf(av2[0], y.x, fmaf(av2[1], y.y, fmaf(av2[2 % DPL], y.z, av2[3 % DPL] * y.w)));
+            } else {
+                const float2 y = *reinterpret_cast<const float2*>(b + j * ld + sub * DPL);
+                s = fmaf(av[0], y.x, av[1] * y.y);
+                if (TWO) s2 = fmaf(av2[0], y.x, av2[1] * y.y);
+            }
+        }
+        part[j] = s;
+        if (TWO) part2[j] = s2;
+    }
+    r = transpose_reduce<LPR>(part, sub);
+    if (TWO) r2 = transpose_reduce<LPR>(reinterpret_cast<float (&)[LPR]>(part2), sub);
+}
 // acc[e] (+)= sum_j w_j * src_j[e]  with w_j taken from lane (group base + j) of `wreg`
 template <int LPR, int DPL>
 __device__ __forceinline__ void group_weighted_rows(float (&acc)[DPL], float wreg, int gbase, const float* __restrict__ src, int ld, int N) {
@@ -441,7 +494,8 @@ __device__ __forceinline__ void attn_forward_rows(Ctx2& c, const LayerDev& W, in
         const int u = valid ? u0 : rows - 1;
         const int r0 = (u / N) * N;
         const bool act = sub < N;
-        const float dot = dot64(c.sQKV + u * C::LDQ, c.sQKV + (r0 + min(sub, N - 1)) * C::LDQ + 64);
+        float dot, dot_unused;
+        group_dots<LPR, DPL, false>(c.sQKV + u * C::LDQ, nullptr, c.sQKV + r0 * C::LDQ + 64, C::LDQ, N, sub, dot, dot_unused);
         const float lg = act ? kAttnScale * dot : -INFINITY;
         const float m = group_max<LPR>(lg);
         const float e = act ? expf(lg - m) : 0.f;
@@ -474,7 +528,8 @@ __device__ __forceinline__ void attn_backward_ds_dq(Ctx2& c, int N, int NP, bool
         const int u = valid ? u0 : rows - 1;
         const int r0 = (u / N) * N;
         const bool act = sub < N;
-        const float dp = dot64(c.sO + u * C::LDO, c.sQKV + (r0 + min(sub, N - 1)) * C::LDQ + 128);
+        float dp, dp_unused;
+        group_dots<LPR, DPL, false>(c.sO + u * C::LDO, nullptr, c.sQKV + r0 * C::LDQ + 128, C::LDQ, N, sub, dp, dp_unused);
         const float p = act ? c.sP[u * NP + sub] : 0.f;
         const float ds = p * (dp - group_sum<LPR>(p * dp));
         if (valid && sub < NP) c.sDS[u * NP + sub] = ds;
@@ -639,7 +694,7 @@ __device__ __forceinline__ void attn_forward_pairs(Ctx2& c, const LayerDev& W, i
         const PairUnit u = pair_unit<C>(base + gid, n_units, pps, N);
         const int ra = u.r0 + u.ia, rb = u.r0 + u.ib;
         float da, db;
-        dot64x2(c.sQKV + ra * C::LDQ, c.sQKV + rb * C::LDQ, c.sQKV + (u.r0 + min(sub, N - 1)) * C::LDQ + 64, da, db);
+        group_dots<LPR, DPL, true>(c.sQKV + ra * C::LDQ, c.sQKV + rb * C::LDQ, c.sQKV + u.r0 * C::LDQ + 64, C::LDQ, N, sub, da, db);
         const float la = act ? kAttnScale * da : -INFINITY, lb = act ? kAttnScale * db : -INFINITY;
         const float ma = group_max<LPR>(la), mb = group_max<LPR>(lb);
         const float ea = act ? expf(la - ma) : 0.f, eb = act ? expf(lb - mb) : 0.f;
@@ -688,7 +743,7 @@ __device__ __forceinline__ void attn_backward_ds_dq_pairs(Ctx2& c, int N, int NP
         const PairUnit u = pair_unit<C>(base + gid, n_units, pps, N);
         const int ra = u.r0 + u.ia, rb = u.r0 + u.ib;
         float dpa, dpb;
-        dot64x2(c.sO + ra * C::LDO, c.sO + rb * C::LDO, c.sQKV + (u.r0 + min(sub, N - 1)) * C::LDQ + 128, dpa, dpb);
+        group_dots<LPR, DPL, true>(c.sO + ra * C::LDO, c.sO + rb * C::LDO, c.sQKV + u.r0 * C::LDQ + 128, C::LDQ, N, sub, dpa, dpb);
         const float pa = act ? c.sP[ra * NP + sub] : 0.f, pb = act ? c.sP[rb * NP + sub] : 0.f;
         const float dsa = pa * (dpa - group_sum<LPR>(pa * dpa)), dsb = pb * (dpb - group_sum<LPR>(pb * dpb));
         if (u.valid && sub < NP) {
@@ -1231,7 +1286,11 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
             const int s0 = g * M.S;
             c.S_act = min(M.S, A.B - s0);
             c.rows_act = c.S_act * N;
+#ifdef DFF_TC_PAIRS_ALWAYS
+            c.pairs = true;
+#else
             c.pairs = c.rows_act > kCW * AttnMap<C>::UPW;
+#endif
             for (int idx = tid; idx < R * 3; idx += kCT) {
                 const int r = idx / 3, cc = idx - r * 3;
                 const bool ok = r < c.rows_act;
