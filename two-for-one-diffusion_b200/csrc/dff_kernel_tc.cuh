@@ -115,8 +115,12 @@ __device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
     asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
     return v;
 }
+// Progress counters (compute -> issuer).  The store is deliberately NOT a release: `st.release.cta` compiles to
+// MEMBAR.ALL.CTA + STS and the membar waits for the signalling warp's outstanding global (stash) stores, ~1k cycles on
+// the critical path of every hand-off.  Ordering is already established: every writer executed fence.proxy.async and
+// the named barrier before thread 0 gets here, so the operand bytes are in shared memory before the counter moves.
 __device__ __forceinline__ void st_release(uint32_t* p, uint32_t v) {
-    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
 }
 // Bounded waits: a protocol bug must fail loudly (trap -> CUDA error -> DFF_ECUDA), never hang the GPU.
 constexpr uint32_t kSpinLimit = 1u << 27;
