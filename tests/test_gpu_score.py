@@ -112,3 +112,35 @@ def test_abi_error_behaviour():
     bad = synthetic_net_params(5, 64, 1, in_edge=1)
     with pytest.raises(DffError, match="intrinsic"):
         ScoreEngine(bad, device="cuda:0")
+
+
+@pytest.mark.parametrize("batch", [2, 6, 40])
+def test_tcgen05_and_mma_sync_kernels_agree(batch, monkeypatch):
+    """Both launch configurations of the same model (tcgen05 / TMEM kernel and the mma.sync kernel) against the fp64
+    oracle and against each other; batch 2 / 6 / 40 exercise the row-local and the pair-local attention routines."""
+    from oracle import collapsed_ref, score_ref
+    p = net_params("chignolin")
+    g = torch.Generator().manual_seed(100 + batch)
+    x = torch.randn(batch, 10, 3, generator=g) * 0.8
+    x = x - x.mean(1, keepdim=True)
+    f64, e64, _ = collapsed_ref.forward_backward(score_ref.to_dtype(p, torch.float64), x.double(), 0.02)
+    out = {}
+    for cfg in ("tc", "legacy"):
+        monkeypatch.setenv("DFF_CONFIG", cfg)
+        eng = _engine(p, max_batch=64)
+        eps, en = eng.score(x.cuda(), 0.02, want_energy=True)
+        assert eng.last_config == ("tc" if cfg == "tc" else eng.last_config) and (cfg != "legacy" or eng.last_config != "tc")
+        assert rel_err(eps, f64) < FORCE_RTOL and rel_err(en, e64) < FORCE_RTOL, (cfg, rel_err(eps, f64))
+        out[cfg] = eps.cpu()
+    assert rel_err(out["tc"], out["legacy"]) < FORCE_RTOL
+
+
+def test_tcgen05_is_the_default_for_hidden_64(monkeypatch):
+    monkeypatch.delenv("DFF_CONFIG", raising=False)
+    eng = _engine(net_params("chignolin"))
+    x = torch.zeros(3, 10, 3, device="cuda")
+    eng.score(x, 0.02)
+    assert eng.last_config == "tc"
+    eng2 = _engine(net_params("trp_cage"))
+    eng2.score(torch.zeros(2, 20, 3, device="cuda"), 0.02)
+    assert eng2.last_config in ("wide", "tall", "duo")
