@@ -79,6 +79,12 @@ int dff_device_count(void);
  * weights_host: array of n_weights host pointers in the order above. */
 int dff_model_create(dff_model_t** out, int device, int num_beads, int hidden, int n_layers,
                      const float* const* weights_host, int n_weights, int max_batch);
+/* Same, for either output head of the reference network (graph_transformer.py:62-65):
+ *   conservative = 1: node_decoder is Linear(H, 1), the prediction is -d sum(E)/dx (hand-written reverse pass);
+ *   conservative = 0: node_decoder is Linear(H, 3) (weights_host[4] is [3, H], weights_host[5] is [3]); the prediction is
+ *                     the decoder output itself, forward only; there is no energy output. */
+int dff_model_create_ex(dff_model_t** out, int device, int num_beads, int hidden, int n_layers,
+                        const float* const* weights_host, int n_weights, int max_batch, int conservative);
 void dff_model_destroy(dff_model_t* m);
 
 /* Shape queries (mirror of the attributes the reference modules expose). */

@@ -144,3 +144,40 @@ def test_tcgen05_is_the_default_for_hidden_64(monkeypatch):
     eng2 = _engine(net_params("trp_cage"))
     eng2.score(torch.zeros(2, 20, 3, device="cuda"), 0.02)
     assert eng2.last_config in ("wide", "tall", "duo")
+
+
+def test_nonconservative_head_vs_reference_golden():
+    """conservative=False nets: the decoder output is the prediction; both kernels (H = 64 -> tcgen05,
+    H = 96 / 128 -> mma.sync), one DDPM step through the sampler, and the energy request must be refused."""
+    from dff_b200 import SCHED_KEYS
+    from dff_b200._native import DffError
+    from oracle import sampler_ref, score_ref
+    from oracle.weights import synthetic_net_params
+    for key, c in load("score_modes.pt").items():
+        p = synthetic_net_params(c["N"], c["H"], c["L"], c["seed"], out_dim=3)
+        eng = _engine(p)
+        assert not eng.conservative
+        x = c["x"].cuda().contiguous()
+        eps, en = eng.score(x, c["t_norm"])
+        assert en is None and rel_err(eps, c["forces"]) < FORCE_RTOL, (key, rel_err(eps, c["forces"]))
+        assert eng.last_config == ("tc" if c["H"] == 64 else eng.last_config)
+        with pytest.raises(DffError):
+            eng.score(x, c["t_norm"], want_energy=True)
+        sched = sampler_ref.cosine_schedule(1000)
+        noise = torch.randn(1, *c["x"].shape, generator=torch.Generator().manual_seed(5))
+        xc = c["x"] - c["x"].mean(1, keepdim=True)
+        ref = sampler_ref.ddpm_step(lambda xx, tn: score_ref.score_forward(p, xx, tn), sched, xc, 400, 1000, noise[0])
+        xd = xc.cuda().contiguous()
+        eng.ddpm_steps(xd, 400, 1, 1000, [sched[k].cuda().contiguous() for k in SCHED_KEYS], noise=noise.cuda().contiguous())
+        assert rel_err(xd, ref) < 2e-4, (key, rel_err(xd, ref))
+
+
+def test_mirror_module_accepts_nonconservative():
+    from models.graph_transformer import GraphTransformer
+    from oracle.weights import synthetic_net_params
+    c = load("score_modes.pt")["nc_N10_H64_L3_s11"]
+    net = GraphTransformer(10, 64, "cuda", n_layers=3, use_intrinsic_coords=True, use_abs_coords=False, use_distances=False,
+                           conservative=False).eval()
+    net.load_state_dict(synthetic_net_params(10, 64, 3, 11, out_dim=3))
+    out = net(c["x"].cuda(), torch.eye(10), torch.full((c["x"].shape[0],), c["t_norm"]))
+    assert rel_err(out, c["forces"]) < FORCE_RTOL

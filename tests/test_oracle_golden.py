@@ -91,3 +91,12 @@ def test_ddpm_full_chain_ala2():
     score = lambda x, tn: score_ref.score_forward(p, x, tn)
     x = sampler_ref.ddpm_sample_loop(score, sched, (2, 5, 3)) * g["meta"]["std"]
     assert rel_err(x, g["sample"]) < 1e-3
+
+
+def test_nonconservative_head_matches_reference():
+    """conservative=False (3-channel decoder, forward only): the literal oracle against the reference's own output
+    (tests/golden/score_modes.pt, made by oracle/make_golden_modes.py with seeded random-init weights)."""
+    for key, c in load("score_modes.pt").items():
+        p = synthetic_net_params(c["N"], c["H"], c["L"], c["seed"], out_dim=3)
+        f = score_ref.score_forward(p, c["x"], c["t_norm"])
+        assert f.shape == c["forces"].shape and rel_err(f, c["forces"]) < 2e-6, (key, rel_err(f, c["forces"]))

@@ -49,6 +49,7 @@ constexpr int ks_for(int nc) { return nc == 384 ? 8 : (nc == 192 ? 16 : (nc == 1
 
 struct dff_model {
     int device = 0, num_sms = 0;
+    int conservative = 1;
     int N = 0, NP = 0, H = 0, HP = 0, L = 0, nch = 0;
     int max_batch = 0;
     float* d_weights = nullptr;     // every packed tensor + GEMM panel
@@ -246,6 +247,11 @@ int dff_device_count(void) {
 
 int dff_model_create(dff_model_t** out, int device, int num_beads, int hidden, int n_layers,
                      const float* const* w, int n_weights, int max_batch) {
+    return dff_model_create_ex(out, device, num_beads, hidden, n_layers, w, n_weights, max_batch, 1);
+}
+
+int dff_model_create_ex(dff_model_t** out, int device, int num_beads, int hidden, int n_layers,
+                        const float* const* w, int n_weights, int max_batch, int conservative) {
     if (!out) return fail(DFF_EINVAL, "out is NULL");
     *out = nullptr;
     const int N = num_beads, H = hidden, L = n_layers;
@@ -270,6 +276,7 @@ int dff_model_create(dff_model_t** out, int device, int num_beads, int hidden, i
     m->device = device; m->num_sms = prop.multiProcessorCount;
     m->N = N; m->NP = (N + 3) / 4 * 4; m->H = H; m->HP = (H <= 64) ? 64 : 128; m->L = L; m->nch = 4 * H / 128;
     m->max_batch = max_batch;
+    m->conservative = conservative ? 1 : 0;
     const int HP = m->HP, nch = m->nch;
     if ((4 * H) % 128) { delete m; return fail(DFF_EINVAL, "4*hidden must be a multiple of 128"); }
 
@@ -279,10 +286,12 @@ int dff_model_create(dff_model_t** out, int device, int num_beads, int hidden, i
     Packer P;
     struct LayerOff { size_t ln1_g, ln1_b, bqkv[2], A, cvec, bo, g1a, g1b, ln2_g, ln2_b, b1, b2, g2a, g2b; };
     std::vector<LayerOff> lo(L);
-    const size_t o_emb = P.alloc((size_t)N * H), o_embt = P.alloc(H), o_dec = P.alloc(H);
+    const int n_dec = conservative ? 1 : 3;                  // node_decoder rows: Linear(H, 1) or Linear(H, 3)
+    const size_t o_emb = P.alloc((size_t)N * H), o_embt = P.alloc(H), o_dec = P.alloc((size_t)n_dec * H);
     for (int i = 0; i < N; ++i)
         for (int d = 0; d < H; ++d) P.buf[o_emb + (size_t)i * H + d] = Wn[(size_t)d * (N + 1) + i] + bn[d];
-    for (int d = 0; d < H; ++d) { P.buf[o_embt + d] = Wn[(size_t)d * (N + 1) + N]; P.buf[o_dec + d] = Wd[d]; }
+    for (int d = 0; d < H; ++d) P.buf[o_embt + d] = Wn[(size_t)d * (N + 1) + N];
+    for (int d = 0; d < n_dec * H; ++d) P.buf[o_dec + d] = Wd[d];
 
     auto LW = [&](int l, int k) { return w[DFF_NUM_GLOBAL_WEIGHTS + DFF_NUM_LAYER_WEIGHTS * l + k]; };
     const int HCs[2] = {2, 1};      // heads per chunk of configuration 0 (R=32) and 1 (R=64)
@@ -504,6 +513,8 @@ int dff_model_create(dff_model_t** out, int device, int num_beads, int hidden, i
         M = ModelDev{};
         M.N = N; M.NP = m->NP; M.H = H; M.L = L; M.S = 1; M.nch = nch;
         M.emb = m->d_weights + o_emb; M.embt = m->d_weights + o_embt; M.dec_w = m->d_weights + o_dec; M.dec_b = bd[0];
+        M.conservative = m->conservative;
+        for (int i = 0; i < 3; ++i) M.dec_b3[i] = conservative ? 0.f : bd[i];
         for (int l = 0; l < L; ++l) {
             const LayerOff& o = lo[l];
             LayerDev& D = M.layer[l];
@@ -553,8 +564,9 @@ double dff_model_flops_per_sample(const dff_model_t* m) {
 int dff_score_dev(dff_model_t* m, const float* x_dev, float t_norm, int batch, float* eps_out_dev,
                   float* energy_out_dev, void* stream) {
     if (!m || !x_dev) return fail(DFF_EINVAL, "NULL model or x");
+    if (!m->conservative && energy_out_dev) return fail(DFF_EINVAL, "a non-conservative network has no energy output (graph_transformer.py:107-113)");
     StepArgs A{};
-    A.mode = MODE_SCORE; A.B = batch; A.n_steps = 1; A.need_backward = eps_out_dev != nullptr;
+    A.mode = MODE_SCORE; A.B = batch; A.n_steps = 1; A.need_backward = m->conservative && eps_out_dev != nullptr;
     A.x = const_cast<float*>(x_dev); A.eps_out = eps_out_dev; A.energy_out = energy_out_dev; A.t_norm = t_norm;
     return launch(m, A, (cudaStream_t)stream);
 }
@@ -583,7 +595,7 @@ int dff_ddpm_steps_dev(dff_model_t* m, float* x_dev, int batch, int t_start, int
         return fail(DFF_EINVAL, "timestep range [%d..%d] outside schedule of length %d", t_start - n_steps + 1, t_start, T);
     if (n_steps == 0) return DFF_OK;
     StepArgs A{};
-    A.mode = MODE_DDPM; A.B = batch; A.n_steps = n_steps; A.need_backward = 1;
+    A.mode = MODE_DDPM; A.B = batch; A.n_steps = n_steps; A.need_backward = m->conservative;
     A.x = x_dev; A.noise = noise_dev; A.t_start = t_start; A.T = T;
     for (int i = 0; i < 5; ++i) { if (!sched_dev[i]) return fail(DFF_EINVAL, "schedule pointer %d is NULL", i); A.sched[i] = sched_dev[i]; }
     A.seed = seed; A.offset = offset; A.flags = flags_dev;
@@ -601,7 +613,7 @@ int dff_langevin_steps_dev(dff_model_t* m, float* x_dev, float* v_dev, int batch
     if (n_steps <= 0) return DFF_OK;
     StepArgs A{};
     A.mode = p->integrator == DFF_MD_BAOAB ? MODE_BAOAB : MODE_BROWNIAN;
-    A.B = batch; A.n_steps = n_steps; A.need_backward = 1;
+    A.B = batch; A.n_steps = n_steps; A.need_backward = m->conservative;
     A.x = x_dev; A.v = (A.mode == MODE_BAOAB) ? v_dev : nullptr; A.noise = noise_dev;
     A.t_norm = p->t_norm; A.force_scale = p->force_scale; A.dt = p->dt; A.vscale = p->vscale; A.noisescale = p->noisescale;
     A.inv_beta = (float)(1.0 / (double)p->beta); A.dtau = p->dtau;

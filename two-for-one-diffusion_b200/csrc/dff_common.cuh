@@ -50,8 +50,10 @@ struct ModelDev {
     int N, NP, H, L, S, nch;        // beads, beads padded to 4, hidden, layers, samples per pass, FF chunks (4H/128)
     const float* emb;               // [N][H]  W_n[:, i] + b_n
     const float* embt;              // [H]     W_n[:, N] (time column)
-    const float* dec_w;             // [H]
+    const float* dec_w;             // [H]      conservative head (energy);  [3][H] for the non-conservative head
     float dec_b;
+    int conservative;               // 1: output = -d sum(E)/dx (reverse pass);  0: output = node_decoder(nodes) [3 channels]
+    float dec_b3[3];
     LayerDev layer[kMaxLayers];
     const Seg* segs;
     int nseg_fwd, nseg_all;

@@ -1330,6 +1330,20 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
                 }
                 csync();
                 if (A.need_backward) backward_pass_tc<C>(M, c);
+                if (!M.conservative) {
+                    // non-conservative head (graph_transformer.py:62-65, 112-113): the prediction is node_decoder(nodes);
+                    // stored negated so that the samplers below read eps = -sDX exactly as in the conservative case
+                    const int lane = tid & 31;
+                    for (int r = warp; r < c.rows_act; r += kCW) {
+                        float s0_ = 0.f, s1_ = 0.f, s2_ = 0.f;
+                        for (int d = lane; d < M.H; d += 32) {
+                            const float v = c.sN[r * C::LDH + d];
+                            s0_ = fmaf(v, __ldg(M.dec_w + d), s0_); s1_ = fmaf(v, __ldg(M.dec_w + M.H + d), s1_); s2_ = fmaf(v, __ldg(M.dec_w + 2 * M.H + d), s2_);
+                        }
+                        s0_ = warp_sum(s0_); s1_ = warp_sum(s1_); s2_ = warp_sum(s2_);
+                        if (lane == 0) { c.sDX[r * 4] = -(s0_ + M.dec_b3[0]); c.sDX[r * 4 + 1] = -(s1_ + M.dec_b3[1]); c.sDX[r * 4 + 2] = -(s2_ + M.dec_b3[2]); }
+                    }
+                }
                 csync();
 
                 if (A.mode == MODE_SCORE) {

@@ -32,6 +32,7 @@ SYMBOLS = {
     "dff_version": (C.c_int, []),
     "dff_device_count": (C.c_int, []),
     "dff_model_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp), C.c_int, C.c_int]),
+    "dff_model_create_ex": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp), C.c_int, C.c_int, C.c_int]),
     "dff_model_destroy": (None, [_vp]),
     "dff_model_num_beads": (C.c_int, [_vp]),
     "dff_model_hidden": (C.c_int, [_vp]),

@@ -51,9 +51,11 @@ class ScoreEngine:
     def __init__(self, state: Dict[str, torch.Tensor], device="cuda:0", max_batch: int = 4096):
         L = count_layers(state)
         H, in_node = state["node_embedding.weight"].shape
-        if state["edge_embedding.weight"].shape[1] != 3 or state["node_decoder.weight"].shape[0] != 1:
-            raise nat.DffError("only conservative intrinsic-coordinate networks (use_intrinsic_coords=True, "
-                               "use_abs_coords=False, use_distances=False, conservative=True) are supported")
+        n_out = state["node_decoder.weight"].shape[0]
+        if state["edge_embedding.weight"].shape[1] != 3 or n_out not in (1, 3):
+            raise nat.DffError("only intrinsic-coordinate networks (use_intrinsic_coords=True, use_abs_coords=False, "
+                               "use_distances=False; conservative or not) are supported")
+        self.conservative = n_out == 1
         self.num_beads, self.hidden, self.n_layers = in_node - 1, H, L
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -63,7 +65,8 @@ class ScoreEngine:
         arr = (C.c_void_p * len(host))(*[t.data_ptr() for t in host])
         h = C.c_void_p()
         idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
-        nat.check(nat.lib().dff_model_create(C.byref(h), idx, self.num_beads, H, L, arr, len(host), self.max_batch))
+        nat.check(nat.lib().dff_model_create_ex(C.byref(h), idx, self.num_beads, H, L, arr, len(host), self.max_batch,
+                                                int(self.conservative)))
         self._h = h
         self._flags = torch.zeros(1, dtype=torch.int32, device=self.device)
 

@@ -67,13 +67,13 @@ class GraphTransformer(nn.Module):
         self.num_beads, self.hidden_nf, self.n_layers = num_beads, hidden_nf, n_layers
         self.use_intrinsic_coords, self.use_distances = use_intrinsic_coords, use_distances
         self.use_abs_coords, self.conservative = use_abs_coords, conservative
-        if not (use_intrinsic_coords and not use_abs_coords and not use_distances and conservative):
-            raise DffError("the B200 kernel implements the configuration of every shipped checkpoint: "
-                           "use_intrinsic_coords=True, use_abs_coords=False, use_distances=False, conservative=True "
-                           "(other edge modes are listed as 'next' in SURVEY.md 8f)")
+        if not (use_intrinsic_coords and not use_abs_coords and not use_distances):
+            raise DffError("the B200 kernels implement the edge mode of every shipped checkpoint: "
+                           "use_intrinsic_coords=True, use_abs_coords=False, use_distances=False (conservative or not); "
+                           "the distance / absolute-coordinate modes are listed as 'next' in SURVEY.md 8f")
         self.node_embedding = nn.Linear(num_beads + 1, hidden_nf)
         self.edge_embedding = nn.Linear(3, hidden_nf)
-        self.node_decoder = nn.Linear(hidden_nf, 1)
+        self.node_decoder = nn.Linear(hidden_nf, 1 if conservative else 3)      # graph_transformer.py:62-65
         self.graphtransformer = GraphTransformerLucid(hidden_nf, n_layers, hidden_nf)
         self.max_batch = 4096
         self._eng, self._eng_key = None, None
@@ -115,5 +115,7 @@ class GraphTransformer(nn.Module):
             raise DffError(f"h must be the [{self.num_beads},{self.num_beads}] bead one-hot matrix")
         eng = self.engine(x.shape[0])
         xin = x.detach().to(eng.device, torch.float32).contiguous()
+        if not self.conservative:       # the decoder output is the prediction; return_energy is ignored (:107-113)
+            return eng.score(xin, self._shared_t(t), want_forces=True, want_energy=False)[0]
         eps, en = eng.score(xin, self._shared_t(t), want_forces=not return_energy, want_energy=return_energy)
         return en.unsqueeze(-1) if return_energy else eps
