@@ -135,20 +135,18 @@ def test_tcgen05_and_mma_sync_kernels_agree(batch, monkeypatch):
     assert rel_err(out["tc"], out["legacy"]) < FORCE_RTOL
 
 
-def test_tcgen05_is_the_default_for_hidden_64(monkeypatch):
+def test_tcgen05_is_the_default_up_to_32_beads(monkeypatch):
+    """hidden 64 / 96 / 128 with N <= 32 run the tcgen05 kernel; protein G (56 beads) stays on the mma.sync kernel."""
     monkeypatch.delenv("DFF_CONFIG", raising=False)
-    eng = _engine(net_params("chignolin"))
-    x = torch.zeros(3, 10, 3, device="cuda")
-    eng.score(x, 0.02)
-    assert eng.last_config == "tc"
-    eng2 = _engine(net_params("trp_cage"))
-    eng2.score(torch.zeros(2, 20, 3, device="cuda"), 0.02)
-    assert eng2.last_config in ("wide", "tall", "duo")
+    for mol, n, want in (("chignolin", 10, "tc"), ("ala2_fold1", 5, "tc"), ("trp_cage", 20, "tc"), ("protein_g", 56, None)):
+        eng = _engine(net_params(mol))
+        eng.score(torch.zeros(2, n, 3, device="cuda"), 0.02)
+        assert (eng.last_config == want) if want else (eng.last_config in ("wide", "tall", "duo")), (mol, eng.last_config)
 
 
 def test_nonconservative_head_vs_reference_golden():
-    """conservative=False nets: the decoder output is the prediction; both kernels (H = 64 -> tcgen05,
-    H = 96 / 128 -> mma.sync), one DDPM step through the sampler, and the energy request must be refused."""
+    """conservative=False nets: the decoder output is the prediction (tcgen05 kernel, hidden 64 / 96 / 128; the
+    mma.sync kernel is covered by the DFF_CONFIG=legacy pass below), one DDPM step, and the energy request must be refused."""
     from dff_b200 import SCHED_KEYS
     from dff_b200._native import DffError
     from oracle import sampler_ref, score_ref
@@ -160,7 +158,7 @@ def test_nonconservative_head_vs_reference_golden():
         x = c["x"].cuda().contiguous()
         eps, en = eng.score(x, c["t_norm"])
         assert en is None and rel_err(eps, c["forces"]) < FORCE_RTOL, (key, rel_err(eps, c["forces"]))
-        assert eng.last_config == ("tc" if c["H"] == 64 else eng.last_config)
+        assert eng.last_config == "tc"
         with pytest.raises(DffError):
             eng.score(x, c["t_norm"], want_energy=True)
         sched = sampler_ref.cosine_schedule(1000)
@@ -181,3 +179,29 @@ def test_mirror_module_accepts_nonconservative():
     net.load_state_dict(synthetic_net_params(10, 64, 3, 11, out_dim=3))
     out = net(c["x"].cuda(), torch.eye(10), torch.full((c["x"].shape[0],), c["t_norm"]))
     assert rel_err(out, c["forces"]) < FORCE_RTOL
+
+
+def test_nonconservative_head_mma_sync_kernel(monkeypatch):
+    from oracle.weights import synthetic_net_params
+    monkeypatch.setenv("DFF_CONFIG", "legacy")
+    for key, c in load("score_modes.pt").items():
+        eng = _engine(synthetic_net_params(c["N"], c["H"], c["L"], c["seed"], out_dim=3))
+        eps, _ = eng.score(c["x"].cuda().contiguous(), c["t_norm"])
+        assert eng.last_config != "tc" and rel_err(eps, c["forces"]) < FORCE_RTOL, (key, rel_err(eps, c["forces"]))
+
+
+@pytest.mark.parametrize("mol", ["ala2_fold1", "trp_cage"])
+def test_tcgen05_and_mma_sync_agree_hidden_96_128(mol, monkeypatch):
+    from oracle import collapsed_ref, score_ref
+    p = net_params(mol)
+    c = load(f"score_{mol}.pt")["cases"][0]
+    f64, e64, _ = collapsed_ref.forward_backward(score_ref.to_dtype(p, torch.float64), c["x"].double(), c["t_norm"])
+    out = {}
+    for cfg in ("tc", "legacy"):
+        monkeypatch.setenv("DFF_CONFIG", cfg)
+        eng = _engine(p)
+        eps, en = eng.score(c["x"].cuda().contiguous(), c["t_norm"], want_energy=True)
+        assert (eng.last_config == "tc") == (cfg == "tc")
+        assert rel_err(eps, f64) < FORCE_RTOL and rel_err(en, e64) < FORCE_RTOL, (cfg, rel_err(eps, f64))
+        out[cfg] = eps.cpu()
+    assert rel_err(out["tc"], out["legacy"]) < FORCE_RTOL

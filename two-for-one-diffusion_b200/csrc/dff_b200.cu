@@ -193,8 +193,12 @@ int launch(dff_model* m, StepArgs& A, cudaStream_t stream) {
         const double slices = (double)((n_groups + grid - 1) / grid) * (double)A.n_steps * (double)m->tc.nslice_all;
         if (slices >= 4.0e9) return fail(DFF_EINVAL, "n_steps %d too large for one launch; split the call (e.g. per save interval)", A.n_steps);
         m->last_R = 64; m->last_S = S; m->last_cfg = "tc";
-        if (m->NP <= 12) return launch_tc<v2::TcCfg<12>>(m, M, A, grid, stream);
-        return launch_tc<v2::TcCfg<32>>(m, M, A, grid, stream);
+        if (m->HP == 64) {
+            if (m->NP <= 12) return launch_tc<v2::TcCfg<12, 64>>(m, M, A, grid, stream);
+            return launch_tc<v2::TcCfg<32, 64>>(m, M, A, grid, stream);
+        }
+        if (m->NP <= 12) return launch_tc<v2::TcCfg<12, 128>>(m, M, A, grid, stream);
+        return launch_tc<v2::TcCfg<32, 128>>(m, M, A, grid, stream);
     }
     int R, S, ctas;
     ModelDev M;
@@ -389,20 +393,20 @@ int dff_model_create_ex(dff_model_t** out, int device, int num_beads, int hidden
     }
 
 
-    // ---- tcgen05 configuration (hidden = 64): job table in issue order + canonical, pre-split weight panels.
-    // A panel is K/ks slices; a slice is [hi image | lo image], each the UMMA K-major no-swizzle layout of a
+    // ---- tcgen05 configuration (hidden 64 / 96 / 128, N <= 32): job table in issue order + canonical, pre-split weight
+    // panels.  A panel is K/ks slices; a slice is [hi image | lo image], each the UMMA K-major no-swizzle layout of a
     // [n rows x ks] tile: float offset ((k / 4) * n + row) * 4 + k % 4.  hi = rn_tf32(w), lo = w - hi.
     struct TcJobHost { size_t offset; v2::TcJob j; };
     std::vector<TcJobHost> tcj;
     int tc_njobs_fwd = 0;
     uint32_t tc_nslice_fwd = 0, tc_nslice_all = 0;
-    const bool tc_shape = (H == 64 && N <= 32);
+    const bool tc_shape = ((H == 64 || H == 96 || H == 128) && N <= 32);
     if (tc_shape) {
-        auto job = [&](int K, int NN, auto&& fill /* (k, n) -> value */, int d_col, int a_slot, int acc_first, int wait_post,
-                       int dbuf, int commit_acc, int commit_d1) {
+        const int stage_bytes = (HP == 64 ? 4096 : 3072) * 4;            // must equal TcCfg::kStageFloats
+        auto job = [&](int K, int NN, auto&& fill /* (k, n) -> value */, int d_col, uint32_t flags) {
             int KS = 8;
-            for (int cand = 8; cand <= K; cand += 8)
-                if (K % cand == 0 && 2 * cand * NN * 4 <= v2::kTcStageFloats * 4) KS = cand;
+            for (int cand = 8; cand <= K && cand <= 248; cand += 8)
+                if (K % cand == 0 && 2 * cand * NN * 4 <= stage_bytes) KS = cand;
             const size_t o = P.alloc((size_t)2 * K * NN);
             for (int k = 0; k < K; ++k)
                 for (int n = 0; n < NN; ++n) {
@@ -419,52 +423,75 @@ int dff_model_create_ex(dff_model_t** out, int device, int num_beads, int hidden
                 }
             TcJobHost h{};
             h.offset = o;
-            h.j.slice_bytes = (uint32_t)(2 * KS * NN * 4);
-            h.j.n_slices = (uint16_t)(K / KS); h.j.ks = (uint16_t)KS; h.j.n = (uint16_t)NN; h.j.d_col = (uint16_t)d_col;
-            h.j.a_slot = (uint8_t)a_slot; h.j.acc_first = (uint8_t)acc_first; h.j.wait_post = (uint8_t)wait_post;
-            h.j.dbuf = (uint8_t)dbuf; h.j.commit_acc = (uint8_t)commit_acc; h.j.commit_d1 = (uint8_t)commit_d1;
+            h.j.slice_16b = (uint16_t)((2 * KS * NN * 4) / 16);
+            h.j.n_slices = (uint8_t)(K / KS); h.j.ks = (uint8_t)KS; h.j.n = (uint16_t)NN; h.j.d_col = (uint16_t)d_col;
+            h.j.flags = (uint8_t)flags;
             tcj.push_back(h);
         };
-        const int cD = (int)v2::kColD, cA = (int)v2::kColAcc;
+        using namespace v2;
+        const int cD = HP, cA = (int)kColAcc;          // TMEM work area starts after the HP-column block accumulator
+        const int nch64 = 4 * H / 64;                  // FF hidden chunks of 64 columns; "supers" of <= 4 chunks share the work area
         for (int l = 0; l < L; ++l) {
             const float *Wq = LW(l, 2), *bq = LW(l, 3), *Wkv = LW(l, 4), *bkv = LW(l, 5), *Wo = LW(l, 8), *W1 = LW(l, 13), *W2 = LW(l, 15);
             const size_t oA = lo[l].A;
-            auto qkv = [&](int hc, int wait_post) {
+            auto qkv = [&](int hc, uint32_t fl) {
                 job(H + 8, 192, [&](int k, int n) -> float {
                     const int t = n / 64, j = hc * 64 + n % 64;
                     if (k < H) return t == 0 ? Wq[(size_t)j * H + k] : Wkv[(size_t)((t == 1 ? 0 : 512) + j) * H + k];
                     if (k < H + 3) return t == 0 ? 0.f : P.buf[oA + (size_t)j * 4 + (k - H)];      // + A x_j  (k', v' only)
                     if (k == H + 3) return t == 0 ? bq[j] : bkv[(t == 1 ? 0 : 512) + j];           // bias rides on the ones column
                     return 0.f;
-                }, cD, 0, 0, wait_post, 1, 0, 0);
+                }, cD, TCJ_DBUF | fl);
             };
-            auto outp = [&](int hc, int commit_acc) {
-                job(64, 64, [&](int k, int d) -> float { return Wo[(size_t)d * 512 + hc * 64 + k]; }, cA, 1, hc > 0, 1, 0, commit_acc, 0);
+            auto outp = [&](int hc) {
+                job(64, HP, [&](int k, int d) -> float { return d < H ? Wo[(size_t)d * 512 + hc * 64 + k] : 0.f; }, cA,
+                    TCJ_SLOT | TCJ_WAIT_POST | (hc > 0 ? TCJ_ACC : 0) | (hc == 7 ? TCJ_COMMIT_ACC : 0));
             };
-            qkv(0, 1); qkv(1, 0);
+            qkv(0, TCJ_WAIT_POST); qkv(1, 0);
             for (int hc = 0; hc < 8; ++hc) {
-                outp(hc, hc == 7);
+                outp(hc);
                 if (hc + 2 < 8) qkv(hc + 2, 0);
             }
-            job(H, 4 * H, [&](int k, int j) -> float { return W1[(size_t)j * H + k]; }, cD, 0, 0, 1, 0, 0, 1);
-            for (int c2 = 0; c2 < 4; ++c2)
-                job(64, 64, [&](int k, int d) -> float { return W2[(size_t)d * 4 * H + c2 * 64 + k]; }, cA, 1, c2 > 0, 1, 0, c2 == 3, 0);
+            // FF1: every super (<= 256 hidden columns) as 128-column jobs into the work area; the first job of a super waits
+            // for a post (LN2 output ready / work area drained), the last one commits d1_ready
+            for (int c0 = 0; c0 < nch64; c0 += 4) {
+                const int w = std::min(4, nch64 - c0) * 64;
+                for (int q = 0; q < w; q += 128) {
+                    const int wq = std::min(128, w - q);
+                    job(H, wq, [&](int k, int j) -> float { return W1[(size_t)(c0 * 64 + q + j) * H + k]; }, cD + q,
+                        (q == 0 ? TCJ_WAIT_POST : 0) | (q + 128 >= w ? TCJ_COMMIT_D1 : 0));
+                }
+            }
+            for (int c2 = 0; c2 < nch64; ++c2)
+                job(64, HP, [&](int k, int d) -> float { return d < H ? W2[(size_t)d * 4 * H + c2 * 64 + k] : 0.f; }, cA,
+                    TCJ_SLOT | TCJ_WAIT_POST | (c2 > 0 ? TCJ_ACC : 0) | (c2 == nch64 - 1 ? TCJ_COMMIT_ACC : 0));
         }
         tc_njobs_fwd = (int)tcj.size();
         for (int l = L - 1; l >= 0; --l) {
             const float *Wq = LW(l, 2), *Wkv = LW(l, 4), *Wo = LW(l, 8), *W1 = LW(l, 13), *W2 = LW(l, 15);
-            job(H, 4 * H, [&](int d, int j) -> float { return W2[(size_t)d * 4 * H + j]; }, cD, 0, 0, 1, 0, 0, 1);
-            for (int c2 = 0; c2 < 4; ++c2)
-                job(64, 64, [&](int j, int d) -> float { return W1[(size_t)(c2 * 64 + j) * H + d]; }, cA, 1, c2 > 0, 1, 0, c2 == 3, 0);
-            auto jdo = [&](int hc, int wait_post) {
-                job(H, 64, [&](int d, int j) -> float { return Wo[(size_t)d * 512 + hc * 64 + j]; }, cD, 0, 0, wait_post, 1, 0, 0);
+            for (int c0 = 0; c0 < nch64; c0 += 4) {
+                const int w = std::min(4, nch64 - c0) * 64;
+                for (int q = 0; q < w; q += 128) {
+                    const int wq = std::min(128, w - q);
+                    job(H, wq, [&](int d, int j) -> float { return W2[(size_t)d * 4 * H + c0 * 64 + q + j]; }, cD + q,
+                        (q == 0 ? TCJ_WAIT_POST : 0) | (q + 128 >= w ? TCJ_COMMIT_D1 : 0));
+                }
+            }
+            for (int c2 = 0; c2 < nch64; ++c2)
+                job(64, HP, [&](int j, int d) -> float { return d < H ? W1[(size_t)(c2 * 64 + j) * H + d] : 0.f; }, cA,
+                    TCJ_SLOT | TCJ_WAIT_POST | (c2 > 0 ? TCJ_ACC : 0) | (c2 == nch64 - 1 ? TCJ_COMMIT_ACC : 0));
+            auto jdo = [&](int hc, uint32_t fl) {
+                job(H, 64, [&](int d, int j) -> float { return Wo[(size_t)d * 512 + hc * 64 + j]; }, cD, TCJ_DBUF | fl);
             };
-            jdo(0, 1); jdo(1, 0);
+            jdo(0, TCJ_WAIT_POST); jdo(1, 0);
             for (int hc = 0; hc < 8; ++hc) {
                 if (l > 0) {
-                    job(64, 64, [&](int j, int d) -> float { return Wq[(size_t)(hc * 64 + j) * H + d]; }, cA, 1, hc > 0, 1, 0, 0, 0);
-                    job(64, 64, [&](int j, int d) -> float { return Wkv[(size_t)(hc * 64 + j) * H + d]; }, cA, 1, 1, 1, 0, 0, 0);
-                    job(64, 64, [&](int j, int d) -> float { return Wkv[(size_t)(512 + hc * 64 + j) * H + d]; }, cA, 1, 1, 1, 0, hc == 7, 0);
+                    job(64, HP, [&](int j, int d) -> float { return d < H ? Wq[(size_t)(hc * 64 + j) * H + d] : 0.f; }, cA,
+                        TCJ_SLOT | TCJ_WAIT_POST | (hc > 0 ? TCJ_ACC : 0));
+                    job(64, HP, [&](int j, int d) -> float { return d < H ? Wkv[(size_t)(hc * 64 + j) * H + d] : 0.f; }, cA,
+                        TCJ_SLOT | TCJ_WAIT_POST | TCJ_ACC);
+                    job(64, HP, [&](int j, int d) -> float { return d < H ? Wkv[(size_t)(512 + hc * 64 + j) * H + d] : 0.f; }, cA,
+                        TCJ_SLOT | TCJ_WAIT_POST | TCJ_ACC | (hc == 7 ? TCJ_COMMIT_ACC : 0));
                 }
                 if (hc + 2 < 8) jdo(hc + 2, 0);
             }
@@ -488,10 +515,10 @@ int dff_model_create_ex(dff_model_t** out, int device, int num_beads, int hidden
 
     if (tc_shape && (int)tcj.size() <= v2::kJobCap) {
         std::vector<v2::TcJob> hj(tcj.size());
-        for (size_t i = 0; i < hj.size(); ++i) { hj[i] = tcj[i].j; hj[i].base = m->d_weights + tcj[i].offset; }
+        for (size_t i = 0; i < hj.size(); ++i) { hj[i] = tcj[i].j; hj[i].w_off = (uint32_t)tcj[i].offset; }
         if (cudaMalloc(&m->d_jobs, hj.size() * sizeof(v2::TcJob)) != cudaSuccess) { cleanup(); return fail(DFF_ENOMEM, "cudaMalloc jobs failed"); }
         if (cudaMemcpy(m->d_jobs, hj.data(), hj.size() * sizeof(v2::TcJob), cudaMemcpyHostToDevice) != cudaSuccess) { cleanup(); return fail(DFF_ECUDA, "job table upload failed"); }
-        m->tc.jobs = m->d_jobs; m->tc.njobs_fwd = tc_njobs_fwd; m->tc.njobs_all = (int)hj.size();
+        m->tc.jobs = m->d_jobs; m->tc.wbase = m->d_weights; m->tc.njobs_fwd = tc_njobs_fwd; m->tc.njobs_all = (int)hj.size();
         m->tc.nslice_fwd = tc_nslice_fwd; m->tc.nslice_all = tc_nslice_all;
         m->tc_ok = true;
 #ifdef DFF_TC_PROFILE
@@ -502,7 +529,7 @@ int dff_model_create_ex(dff_model_t** out, int device, int num_beads, int hidden
 
     stash_geometry(32, m->NP, H, m->off[0], &m->layer_floats[0]);
     stash_geometry(64, m->NP, H, m->off[1], &m->layer_floats[1]);
-    m->scratch_per_cta = (long long)L * m->layer_floats[1] + 64LL * H;
+    m->scratch_per_cta = (long long)L * m->layer_floats[1] + 64LL * H + 64LL * (128 + 4);   // + node stream [64][132] (tc kernel, hidden > 64)
     const int n_ctas = std::min(2 * m->num_sms, std::max(1, max_batch));
     m->scratch_ctas = n_ctas;
     if (cudaMalloc(&m->d_scratch, (size_t)n_ctas * m->scratch_per_cta * sizeof(float)) != cudaSuccess) { cleanup(); return fail(DFF_ENOMEM, "cudaMalloc scratch failed"); }

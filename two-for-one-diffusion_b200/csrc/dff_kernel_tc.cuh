@@ -38,53 +38,63 @@ constexpr int kCT = kCW * 32;                      // compute threads
 constexpr int kComputeThreads = kCT;
 constexpr int kTcThreads = kComputeThreads + 64;   // + TMA producer warp + MMA issuer warp
 constexpr int kTcStages = 3;
-constexpr int kTcStageFloats = 4096;      // 16 KB: the largest slice, [hi|lo] x [8 k][256 n]
 constexpr int kCS = kR * 4 + 4;           // canonical chunk stride in floats (64 rows x 16 B + 16 B pad: bank spread)
-constexpr int kJobCap = 160;              // job-table entries cached in shared memory
+constexpr int kJobCap = 200;              // job-table entries (16 B each) cached in shared memory
 
-// TMEM column map (fp32 columns, 64 lanes used)
-constexpr uint32_t kColAcc = 0;           // [64]  att / ff / d m_hat / d n_hat accumulator
-constexpr uint32_t kColD = 64;            // [2 x 192] q|k'|v' double buffer, [256] FF hidden, [2 x 64] d o double buffer
+// TMEM column map (fp32 columns, 64 lanes used): [0, HP) block accumulator (att / ff / d m_hat / d n_hat), then at HP the
+// work area: 2 x 192 q|k'|v' double buffer, <= 256 columns of FF hidden, 2 x 64 d o double buffer.   HP + 384 <= 512.
+constexpr uint32_t kColAcc = 0;
 constexpr uint32_t kTmemCols = 512;
 
-// One GEMM of the per-step schedule, in issue order (built by the host, dff_b200.cu: build_tc_jobs).
+// One GEMM of the per-step schedule, in issue order (built by the host, dff_b200.cu).  16 bytes.
 struct TcJob {
-    const float* base;        // weight panel: n_slices contiguous slices, each [hi image | lo image] of [ks/4][n][4] floats
-    uint32_t slice_bytes;
-    uint16_t n_slices, ks;
-    uint16_t n;               // MMA N (64, 192, 256)
+    uint32_t w_off;           // weight panel (floats from TcArgs::wbase): n_slices contiguous slices, each
+                              // [hi image | lo image] of [ks/4][n][4] floats
+    uint16_t slice_16b;       // slice size in 16-byte units
+    uint8_t n_slices, ks;
+    uint16_t n;               // MMA N (64, 128, 192)
     uint16_t d_col;           // TMEM column of D (double-buffered jobs: column of buffer 0)
-    uint8_t a_slot;           // 0: A operand = the persistent buffer (n_hat / d ff / d att), 1: the rotating slot
-    uint8_t acc_first;        // 0: first MMA overwrites D, 1: accumulates
-    uint8_t wait_post;        // 1: wait for the next "operand ready" post of the compute warps before issuing
-    uint8_t dbuf;             // 1: D is double-buffered (QKV / d o jobs): gate on the drain counter, commit -> dq_ready[parity]
-    uint8_t commit_acc;       // 1: commit -> acc_ready after the job
-    uint8_t commit_d1;        // 1: commit -> d1_ready after the job
-    uint8_t pad_[2];
+    uint8_t flags;            // TCJ_*
+    uint8_t pad_[3];
 };
-static_assert(sizeof(TcJob) == 32, "TcJob layout");
+static_assert(sizeof(TcJob) == 16, "TcJob layout");
+enum : uint32_t {
+    TCJ_SLOT = 1,             // A operand = the rotating slot (else the persistent buffer: n_hat / d ff / d att)
+    TCJ_ACC = 2,              // first MMA accumulates (else overwrites D)
+    TCJ_WAIT_POST = 4,        // wait for the next "operand ready" post of the compute warps before issuing
+    TCJ_DBUF = 8,             // D is double-buffered (QKV / d o jobs): gate on the drain counter, commit -> dq_ready[parity]
+    TCJ_COMMIT_ACC = 16,      // commit -> acc_ready after the job
+    TCJ_COMMIT_D1 = 32,       // commit -> d1_ready after the job
+};
 
 struct TcArgs {
     const TcJob* jobs;
+    const float* wbase;
     int njobs_fwd, njobs_all;
     uint32_t nslice_fwd, nslice_all;
     long long* dbg;           // [grid][16] wait-cycle counters (DFF_TC_PROFILE builds), else NULL
 };
 
-// ------------------------------------------------------------------ configuration (hidden = 64)
-template <int PN_>
+// ------------------------------------------------------------------ configuration
+// HP = 64 (hidden 64) keeps the node stream in shared memory and uses 16 KB weight stages; HP = 128 (hidden 96 / 128) keeps
+// the node stream in the per-CTA global scratch (row passes only, coalesced, L2 resident) and uses 12 KB stages -- that is
+// what lets the fp32 hi/lo operands of a 64-row tile (8 bytes per element) fit 227 KB.
+template <int PN_, int HP_>
 struct TcCfg {
-    static constexpr int kHP = 64, kR = v2::kR, kHC = 1, kPN = PN_;
+    static constexpr int kHP = HP_, kR = v2::kR, kHC = 1, kPN = PN_;
     static constexpr int CWQ = 64, NCH = kHeads;
     static constexpr int LDH = kHP + 4;
     static constexpr int LDQ = 3 * CWQ + 4;
     static constexpr int LDO = CWQ + 4;
     static constexpr int EPL = kHP / 32;
-    static constexpr int NHAT_CHUNKS = kHP / 4 + 2;          // + [x0 x1 x2 1] chunk + zero chunk (K = 72 for the QKV jobs)
+    static constexpr int NHAT_CHUNKS = kHP / 4 + 2;          // + [x0 x1 x2 1] chunk + zero chunk (K = H + 8 for the QKV jobs)
     static constexpr int SLOT_CHUNKS = 16;
+    static constexpr bool kNodeInSmem = (kHP == 64);
+    static constexpr int kStageFloats = (kHP == 64) ? 4096 : 3072;
+    static constexpr uint32_t kColD = kHP;                   // TMEM work area
     // shared memory carve-up (float offsets)
-    static constexpr int oN = 0;                             // [R][LDH] node stream / its gradient
-    static constexpr int oQKV = oN + kR * LDH;               // [R][LDQ] q|k'|v' of the head chunk; also the [R][LDH] row buffer
+    static constexpr int oN = 0;                             // [R][LDH] node stream / its gradient (HP = 64 only)
+    static constexpr int oQKV = oN + (kNodeInSmem ? kR * LDH : 0);   // [R][LDQ] q|k'|v' of the head chunk; also the [R][LDH] row buffer
     static constexpr int oO = oQKV + kR * LDQ;               // [R][LDO] d o of the head chunk (reverse pass)
     static constexpr int oP = oO + kR * LDO;
     static constexpr int oDS = oP + kR * kPN;
@@ -93,16 +103,18 @@ struct TcCfg {
     static constexpr int oSlotHi = oNhatLo + NHAT_CHUNKS * kCS;   // canonical rotating A operand
     static constexpr int oSlotLo = oSlotHi + SLOT_CHUNKS * kCS;
     static constexpr int oW = oSlotLo + SLOT_CHUNKS * kCS;   // weight ring
-    static constexpr int oX = oW + kTcStages * kTcStageFloats;
+    static constexpr int oX = oW + kTcStages * kStageFloats;
     static constexpr int oV = oX + kR * 4;
     static constexpr int oDX = oV + kR * 4;
     static constexpr int oTmp = oDX + kR * 4;
     static constexpr int oJobs = oTmp + kR * 4;
-    static constexpr int oBar = oJobs + kJobCap * 8;
+    static constexpr int oBar = oJobs + kJobCap * 4;
     static constexpr int kFloats = oBar + 32;
     static constexpr size_t kSmemBytes = (size_t)kFloats * sizeof(float);
+    static_assert(kR * LDH <= kR * LDQ, "row buffer must fit the q|k'|v' buffer");
     static_assert(oNhatHi % 4 == 0 && oSlotHi % 4 == 0 && oW % 4 == 0 && oJobs % 4 == 0 && oBar % 4 == 0, "16-byte alignment");
     static_assert(kSmemBytes <= 232448, "exceeds the 227 KB dynamic shared memory limit");
+    static_assert(kColD + 384 <= kTmemCols, "TMEM column budget");
 };
 
 // barrier / counter block at oBar (uint64 slots)
@@ -264,20 +276,74 @@ struct Ctx2 {
 
 // ------------------------------------------------------------------ warp-per-row phases writing canonical operands
 // (only the active rows are processed; pad rows of the operands hold stale finite values whose products are never read)
+// A lane owns E = HP / 32 consecutive columns of its row: E = 2 (hidden 64) or 4 (hidden 96 / 128; lanes beyond H idle).
+template <int E> struct RowVec { float v[E]; };
+template <int E>
+__device__ __forceinline__ RowVec<E> row_ld(const float* p, bool ok) {
+    RowVec<E> r;
+    if (ok) {
+        if (E == 4) { const float4 t = *reinterpret_cast<const float4*>(p); r.v[0] = t.x; r.v[1] = t.y; r.v[2 % E] = t.z; r.v[3 % E] = t.w; }
+        else { const float2 t = *reinterpret_cast<const float2*>(p); r.v[0] = t.x; r.v[1] = t.y; }
+    } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) r.v[e] = 0.f;
+    }
+    return r;
+}
+template <int E>
+__device__ __forceinline__ RowVec<E> row_ldg(const float* __restrict__ p, bool ok) {
+    RowVec<E> r;
+    if (ok) {
+        if (E == 4) { const float4 t = __ldg(reinterpret_cast<const float4*>(p)); r.v[0] = t.x; r.v[1] = t.y; r.v[2 % E] = t.z; r.v[3 % E] = t.w; }
+        else { const float2 t = __ldg(reinterpret_cast<const float2*>(p)); r.v[0] = t.x; r.v[1] = t.y; }
+    } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) r.v[e] = 0.f;
+    }
+    return r;
+}
+template <int E>
+__device__ __forceinline__ void row_st(float* p, const RowVec<E>& r) {
+    if (E == 4) *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2 % E], r.v[3 % E]);
+    else *reinterpret_cast<float2*>(p) = make_float2(r.v[0], r.v[1]);
+}
+template <int E>
+__device__ __forceinline__ void row_can_store(float* hi, float* lo, int r, int col, const RowVec<E>& x) {
+    if (E == 4) can_store4(hi, lo, r, col >> 2, make_float4(x.v[0], x.v[1], x.v[2 % E], x.v[3 % E]));
+    else can_store2(hi, lo, r, col, x.v[0], x.v[1]);
+}
+template <int E>
+__device__ __forceinline__ float row_sum(const RowVec<E>& x) {
+    float s = 0.f;
+#pragma unroll
+    for (int e = 0; e < E; ++e) s += x.v[e];
+    return s;
+}
+
 // LayerNorm of sN rows -> canonical n_hat; stats -> stash; stashes the input rows.
 template <class C>
 __device__ __forceinline__ void ln_forward_rows_can(const float* sN, float* hi, float* lo, const float* __restrict__ gam,
                                                     const float* __restrict__ bet, int H, int rows, float* st_rows, float* st_stats) {
+    constexpr int E = C::EPL;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int col = lane * E;
+    const bool ok = col < H;
     for (int r = warp; r < rows; r += kCW) {
-        const int col = lane * 2;
-        const float2 x = *reinterpret_cast<const float2*>(sN + r * C::LDH + col);
-        const float mean = warp_sum(x.x + x.y) / (float)H;
-        const float d0 = x.x - mean, d1 = x.y - mean;
-        const float rstd = 1.0f / sqrtf(warp_sum(d0 * d0 + d1 * d1) / (float)H + kLnEps);
-        const float2 g = __ldg(reinterpret_cast<const float2*>(gam + col)), b = __ldg(reinterpret_cast<const float2*>(bet + col));
-        can_store2(hi, lo, r, col, d0 * rstd * g.x + b.x, d1 * rstd * g.y + b.y);
-        *reinterpret_cast<float2*>(st_rows + (size_t)r * H + col) = x;
+        const RowVec<E> x = row_ld<E>(sN + r * C::LDH + col, ok);
+        const float mean = warp_sum(row_sum<E>(x)) / (float)H;
+        RowVec<E> d;
+        float q = 0.f;
+#pragma unroll
+        for (int e = 0; e < E; ++e) { d.v[e] = ok ? x.v[e] - mean : 0.f; q += d.v[e] * d.v[e]; }
+        const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)H + kLnEps);
+        if (ok) {
+            const RowVec<E> g = row_ldg<E>(gam + col, true), b = row_ldg<E>(bet + col, true);
+            RowVec<E> y;
+#pragma unroll
+            for (int e = 0; e < E; ++e) y.v[e] = d.v[e] * rstd * g.v[e] + b.v[e];
+            row_can_store<E>(hi, lo, r, col, y);
+            row_st<E>(st_rows + (size_t)r * H + col, x);
+        }
         if (lane == 0) { st_stats[r * 2] = mean; st_stats[r * 2 + 1] = rstd; }
     }
 }
@@ -290,25 +356,41 @@ __device__ __forceinline__ void gate_ln_forward_rows_can(float* sN, const float*
                                                          float* st_a, float* st_g, float* st_out,
                                                          const float* __restrict__ gam, const float* __restrict__ bet,
                                                          float* st_stats) {
+    constexpr int E = C::EPL;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int col = lane * E;
+    const bool ok = col < H;
     for (int r = warp; r < rows; r += kCW) {
-        const int col = lane * 2;
-        const float2 a = *reinterpret_cast<const float2*>(sA + r * C::LDH + col);
-        const float2 n = *reinterpret_cast<const float2*>(sN + r * C::LDH + col);
-        const float2 wa = __ldg(reinterpret_cast<const float2*>(ga + col)), wb = __ldg(reinterpret_cast<const float2*>(gb + col));
-        const float z = warp_sum(a.x * wa.x + n.x * wb.x + a.y * wa.y + n.y * wb.y);
+        const RowVec<E> a = row_ld<E>(sA + r * C::LDH + col, ok), n = row_ld<E>(sN + r * C::LDH + col, ok);
+        const RowVec<E> wa = row_ldg<E>(ga + col, ok), wb = row_ldg<E>(gb + col, ok);
+        float z = 0.f;
+#pragma unroll
+        for (int e = 0; e < E; ++e) z += a.v[e] * wa.v[e] + n.v[e] * wb.v[e];
+        z = warp_sum(z);
         const float g = 1.0f / (1.0f + expf(-z));
-        const float2 o = make_float2(a.x * g + n.x * (1.0f - g), a.y * g + n.y * (1.0f - g));
-        *reinterpret_cast<float2*>(st_a + (size_t)r * H + col) = a;
-        *reinterpret_cast<float2*>(st_out + (size_t)r * H + col) = o;
-        *reinterpret_cast<float2*>(sN + r * C::LDH + col) = o;
+        RowVec<E> o;
+#pragma unroll
+        for (int e = 0; e < E; ++e) o.v[e] = a.v[e] * g + n.v[e] * (1.0f - g);
+        if (ok) {
+            row_st<E>(st_a + (size_t)r * H + col, a);
+            row_st<E>(st_out + (size_t)r * H + col, o);
+            row_st<E>(sN + r * C::LDH + col, o);
+        }
         if (lane == 0) st_g[r] = g;
         if (gam == nullptr) continue;
-        const float mean = warp_sum(o.x + o.y) / (float)H;
-        const float d0 = o.x - mean, d1 = o.y - mean;
-        const float rstd = 1.0f / sqrtf(warp_sum(d0 * d0 + d1 * d1) / (float)H + kLnEps);
-        const float2 gg = __ldg(reinterpret_cast<const float2*>(gam + col)), bb = __ldg(reinterpret_cast<const float2*>(bet + col));
-        can_store2(hi, lo, r, col, d0 * rstd * gg.x + bb.x, d1 * rstd * gg.y + bb.y);
+        const float mean = warp_sum(row_sum<E>(o)) / (float)H;
+        RowVec<E> d;
+        float q = 0.f;
+#pragma unroll
+        for (int e = 0; e < E; ++e) { d.v[e] = ok ? o.v[e] - mean : 0.f; q += d.v[e] * d.v[e]; }
+        const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)H + kLnEps);
+        if (ok) {
+            const RowVec<E> gg = row_ldg<E>(gam + col, true), bb = row_ldg<E>(bet + col, true);
+            RowVec<E> y;
+#pragma unroll
+            for (int e = 0; e < E; ++e) y.v[e] = d.v[e] * rstd * gg.v[e] + bb.v[e];
+            row_can_store<E>(hi, lo, r, col, y);
+        }
         if (lane == 0) { st_stats[r * 2] = mean; st_stats[r * 2 + 1] = rstd; }
     }
 }
@@ -322,30 +404,44 @@ __device__ __forceinline__ void gate_backward_rows_can(float* sN, const float* s
                                                        const float* st_stats, const float* st_a, const float* st_n,
                                                        const float* st_g, const float* __restrict__ ga,
                                                        const float* __restrict__ gb) {
+    constexpr int E = C::EPL;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int col = lane * E;
+    const bool ok = col < H;
     for (int r = warp; r < rows; r += kCW) {
-        const int col = lane * 2;
-        const float2 a = *reinterpret_cast<const float2*>(st_a + (size_t)r * H + col);
-        const float2 n = *reinterpret_cast<const float2*>(st_n + (size_t)r * H + col);
-        float2 d = *reinterpret_cast<const float2*>(sN + r * C::LDH + col);
+        const RowVec<E> a = row_ld<E>(st_a + (size_t)r * H + col, ok), n = row_ld<E>(st_n + (size_t)r * H + col, ok);
+        RowVec<E> d = row_ld<E>(sN + r * C::LDH + col, ok);
         const float g = st_g[r];
         if (gam != nullptr) {
             const float mean = st_stats[r * 2], rstd = st_stats[r * 2 + 1];
-            const float2 xin = *reinterpret_cast<const float2*>(st_ln_in + (size_t)r * H + col);
-            const float2 dd = *reinterpret_cast<const float2*>(sD + r * C::LDH + col);
-            const float2 gg = __ldg(reinterpret_cast<const float2*>(gam + col));
-            const float y0 = (xin.x - mean) * rstd, y1 = (xin.y - mean) * rstd;
-            const float dy0 = dd.x * gg.x, dy1 = dd.y * gg.y;
-            const float s1 = warp_sum(dy0 + dy1) / (float)H;
-            const float s2 = warp_sum(dy0 * y0 + dy1 * y1) / (float)H;
-            d.x += rstd * (dy0 - s1 - y0 * s2);
-            d.y += rstd * (dy1 - s1 - y1 * s2);
+            const RowVec<E> xin = row_ld<E>(st_ln_in + (size_t)r * H + col, ok), dd = row_ld<E>(sD + r * C::LDH + col, ok);
+            const RowVec<E> gg = row_ldg<E>(gam + col, ok);
+            RowVec<E> y, dy;
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                y.v[e] = ok ? (xin.v[e] - mean) * rstd : 0.f;
+                dy.v[e] = dd.v[e] * gg.v[e];
+                s1 += dy.v[e]; s2 += dy.v[e] * y.v[e];
+            }
+            s1 = warp_sum(s1) / (float)H;
+            s2 = warp_sum(s2) / (float)H;
+#pragma unroll
+            for (int e = 0; e < E; ++e) if (ok) d.v[e] += rstd * (dy.v[e] - s1 - y.v[e] * s2);
         }
-        const float dg = warp_sum(d.x * (a.x - n.x) + d.y * (a.y - n.y));
+        float dg = 0.f;
+#pragma unroll
+        for (int e = 0; e < E; ++e) dg += d.v[e] * (a.v[e] - n.v[e]);
+        dg = warp_sum(dg);
         const float dz = dg * g * (1.0f - g);
-        const float2 wa = __ldg(reinterpret_cast<const float2*>(ga + col)), wb = __ldg(reinterpret_cast<const float2*>(gb + col));
-        can_store2(hi, lo, r, col, d.x * g + dz * wa.x, d.y * g + dz * wa.y);
-        *reinterpret_cast<float2*>(sN + r * C::LDH + col) = make_float2(d.x * (1.0f - g) + dz * wb.x, d.y * (1.0f - g) + dz * wb.y);
+        if (ok) {
+            const RowVec<E> wa = row_ldg<E>(ga + col, true), wb = row_ldg<E>(gb + col, true);
+            RowVec<E> da, dn;
+#pragma unroll
+            for (int e = 0; e < E; ++e) { da.v[e] = d.v[e] * g + dz * wa.v[e]; dn.v[e] = d.v[e] * (1.0f - g) + dz * wb.v[e]; }
+            row_can_store<E>(hi, lo, r, col, da);
+            row_st<E>(sN + r * C::LDH + col, dn);
+        }
     }
 }
 
@@ -353,21 +449,30 @@ __device__ __forceinline__ void gate_backward_rows_can(float* sN, const float* s
 template <class C>
 __device__ __forceinline__ void ln_backward_rows_tc(float* sN, const float* sD, int H, int rows, const float* __restrict__ gam,
                                                     const float* st_ln_in, const float* st_stats) {
+    constexpr int E = C::EPL;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int col = lane * E;
+    const bool ok = col < H;
     for (int r = warp; r < rows; r += kCW) {
-        const int col = lane * 2;
         const float mean = st_stats[r * 2], rstd = st_stats[r * 2 + 1];
-        const float2 xin = *reinterpret_cast<const float2*>(st_ln_in + (size_t)r * H + col);
-        const float2 dd = *reinterpret_cast<const float2*>(sD + r * C::LDH + col);
-        const float2 gg = __ldg(reinterpret_cast<const float2*>(gam + col));
-        const float y0 = (xin.x - mean) * rstd, y1 = (xin.y - mean) * rstd;
-        const float dy0 = dd.x * gg.x, dy1 = dd.y * gg.y;
-        const float s1 = warp_sum(dy0 + dy1) / (float)H;
-        const float s2 = warp_sum(dy0 * y0 + dy1 * y1) / (float)H;
-        float2 d = *reinterpret_cast<const float2*>(sN + r * C::LDH + col);
-        d.x += rstd * (dy0 - s1 - y0 * s2);
-        d.y += rstd * (dy1 - s1 - y1 * s2);
-        *reinterpret_cast<float2*>(sN + r * C::LDH + col) = d;
+        const RowVec<E> xin = row_ld<E>(st_ln_in + (size_t)r * H + col, ok), dd = row_ld<E>(sD + r * C::LDH + col, ok);
+        const RowVec<E> gg = row_ldg<E>(gam + col, ok);
+        RowVec<E> y, dy;
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            y.v[e] = ok ? (xin.v[e] - mean) * rstd : 0.f;
+            dy.v[e] = dd.v[e] * gg.v[e];
+            s1 += dy.v[e]; s2 += dy.v[e] * y.v[e];
+        }
+        s1 = warp_sum(s1) / (float)H;
+        s2 = warp_sum(s2) / (float)H;
+        if (ok) {
+            RowVec<E> d = row_ld<E>(sN + r * C::LDH + col, true);
+#pragma unroll
+            for (int e = 0; e < E; ++e) d.v[e] += rstd * (dy.v[e] - s1 - y.v[e] * s2);
+            row_st<E>(sN + r * C::LDH + col, d);
+        }
     }
 }
 
@@ -886,13 +991,13 @@ __device__ void forward_pass_tc(const ModelDev& M, Ctx2& c, float t_norm) {
     // layer-0 node stream: W_n [onehot_i, t] + b_n   (graph_transformer.py:99-103)
     for (int idx = tid; idx < rows * C::kHP; idx += kCT) {
         const int r = idx / C::kHP, d = idx - r * C::kHP;
-        c.sN[r * C::LDH + d] = __ldg(M.emb + (r % N) * H + d) + t_norm * __ldg(M.embt + d);
+        c.sN[r * C::LDH + d] = (d < H) ? __ldg(M.emb + (r % N) * H + d) + t_norm * __ldg(M.embt + d) : 0.f;
     }
     // augmented operand columns of this step: [x0 x1 x2 1] (chunk H/4); chunk H/4 + 1 stays zero
     if (tid < R) {
         const float4 xv = (tid < rows) ? make_float4(c.sX[tid * 4], c.sX[tid * 4 + 1], c.sX[tid * 4 + 2], 1.0f)
                                        : make_float4(0.f, 0.f, 0.f, 0.f);
-        can_store4(c.nhat_hi, c.nhat_lo, tid, C::kHP / 4, xv);
+        can_store4(c.nhat_hi, c.nhat_lo, tid, H / 4, xv);
     }
     csync();
     ln_forward_rows_can<C>(c.sN, c.nhat_hi, c.nhat_lo, M.layer[0].ln1_g, M.layer[0].ln1_b, H, rows, c.stash + M.off[ST_NIN],
@@ -909,7 +1014,7 @@ __device__ void forward_pass_tc(const ModelDev& M, Ctx2& c, float t_norm) {
                 const int b = c.dq_wait();
                 c.mark(1);
                 float* st_qkv = st + M.off[ST_QKV] + (size_t)hc * R * 3 * C::CWQ;
-                tmem_foreach<192>(c.tmem, kColD + b * 192, rows, [&](int row, int col, const float (&v)[16]) {
+                tmem_foreach<192>(c.tmem, C::kColD + b * 192, rows, [&](int row, int col, const float (&v)[16]) {
 #pragma unroll
                     for (int i = 0; i < 16; i += 4) {
                         const float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
@@ -930,7 +1035,7 @@ __device__ void forward_pass_tc(const ModelDev& M, Ctx2& c, float t_norm) {
         // attention block output -> row buffer; gated residual 1 + LayerNorm 2 -> canonical operand of FF1
         c.acc_wait();
         c.mark(5);
-        tmem_foreach<64>(c.tmem, kColAcc, rows, [&](int row, int col, const float (&v)[16]) {
+        tmem_foreach<C::kHP>(c.tmem, kColAcc, rows, [&](int row, int col, const float (&v)[16]) {
 #pragma unroll
             for (int i = 0; i < 16; i += 4) {
                 const float4 b = __ldg(reinterpret_cast<const float4*>(W.bo + col + i));
@@ -945,46 +1050,52 @@ __device__ void forward_pass_tc(const ModelDev& M, Ctx2& c, float t_norm) {
         c.post();
         c.mark(7);
 
-        // feed-forward: hidden pre-activations [rows][4H] TMEM -> shared once; then bias + GELU 64 columns at a time,
-        // spread over all threads -> slot -> FF2 accumulates
-        c.d1_wait();
-        c.mark(8);
+        // feed-forward: hidden pre-activations TMEM -> shared, up to 256 columns ("super") at a time; then bias + GELU
+        // 64 columns at a time, spread over all threads -> slot -> FF2 accumulates
         float* sH = c.sQKV;
-        tmem_foreach<256>(c.tmem, kColD, rows, [&](int row, int col, const float (&v)[16]) {
+        const int nch64 = (4 * H) / 64;
+        for (int c0 = 0; c0 < nch64; c0 += 4) {
+            const int nc = min(4, nch64 - c0);
+            c.d1_wait();
+            c.mark(8);
+            tmem_foreach<256>(c.tmem, C::kColD, rows, [&](int row, int col, const float (&v)[16]) {
 #pragma unroll
-            for (int i = 0; i < 16; i += 4)
-                *reinterpret_cast<float4*>(sH + row * kLDF + col + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-        });
-        tc::fence_before_sync();
-        csync();
-        c.mark(9);
-        for (int ch = 0; ch < 4; ++ch) {
-            constexpr int MG = (R * 16) / kCT;       // granules (row, 4 columns) per thread
-            float4 gq[MG];
+                for (int i = 0; i < 16; i += 4)
+                    *reinterpret_cast<float4*>(sH + row * kLDF + col + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            });
+            tc::fence_before_sync();
+            csync();
+            if (c0 + 4 < nch64) c.post();            // TMEM work area drained: the issuer may start the next super's FF1
+            c.mark(9);
+            for (int ch = 0; ch < nc; ++ch) {
+                constexpr int MG = (R * 16) / kCT;       // granules (row, 4 columns) per thread
+                const int gc = (c0 + ch) * 64;           // hidden column of the chunk
+                float4 gq[MG];
 #pragma unroll
-            for (int g = 0; g < MG; ++g) {
-                const int idx = tid + g * kCT;
-                if (idx < rows * 16) {
-                    const int r = idx >> 4, k4 = idx & 15;
-                    const float4 v = *reinterpret_cast<const float4*>(sH + r * kLDF + ch * 64 + k4 * 4);
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(W.b1 + ch * 64 + k4 * 4));
-                    const float4 pre = make_float4(v.x + b.x, v.y + b.y, v.z + b.z, v.w + b.w);
-                    *reinterpret_cast<float4*>(st + M.off[ST_H1] + (size_t)r * (4 * H) + ch * 64 + k4 * 4) = pre;
-                    gq[g] = make_float4(gelu_f(pre.x), gelu_f(pre.y), gelu_f(pre.z), gelu_f(pre.w));
+                for (int g = 0; g < MG; ++g) {
+                    const int idx = tid + g * kCT;
+                    if (idx < rows * 16) {
+                        const int r = idx >> 4, k4 = idx & 15;
+                        const float4 v = *reinterpret_cast<const float4*>(sH + r * kLDF + ch * 64 + k4 * 4);
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(W.b1 + gc + k4 * 4));
+                        const float4 pre = make_float4(v.x + b.x, v.y + b.y, v.z + b.z, v.w + b.w);
+                        *reinterpret_cast<float4*>(st + M.off[ST_H1] + (size_t)r * (4 * H) + gc + k4 * 4) = pre;
+                        gq[g] = make_float4(gelu_f(pre.x), gelu_f(pre.y), gelu_f(pre.z), gelu_f(pre.w));
+                    }
                 }
-            }
-            c.slot_acquire();
+                c.slot_acquire();
 #pragma unroll
-            for (int g = 0; g < MG; ++g) {
-                const int idx = tid + g * kCT;
-                if (idx < rows * 16) can_store4(c.slot_hi, c.slot_lo, idx >> 4, idx & 15, gq[g]);
+                for (int g = 0; g < MG; ++g) {
+                    const int idx = tid + g * kCT;
+                    if (idx < rows * 16) can_store4(c.slot_hi, c.slot_lo, idx >> 4, idx & 15, gq[g]);
+                }
+                c.slot_post();
             }
-            c.slot_post();
         }
         c.mark(10);
         c.acc_wait();
         c.mark(5);
-        tmem_foreach<64>(c.tmem, kColAcc, rows, [&](int row, int col, const float (&v)[16]) {
+        tmem_foreach<C::kHP>(c.tmem, kColAcc, rows, [&](int row, int col, const float (&v)[16]) {
 #pragma unroll
             for (int i = 0; i < 16; i += 4) {
                 const float4 b = __ldg(reinterpret_cast<const float4*>(W.b2 + col + i));
@@ -1014,7 +1125,7 @@ __device__ void backward_pass_tc(const ModelDev& M, Ctx2& c) {
 
     for (int idx = tid; idx < rows * C::kHP; idx += kCT) {
         const int r = idx / C::kHP, d = idx - r * C::kHP;
-        c.sN[r * C::LDH + d] = __ldg(M.dec_w + d);               // dE_r/dn_r = w_dec  (node_decoder, :106)
+        c.sN[r * C::LDH + d] = (d < H) ? __ldg(M.dec_w + d) : 0.f;      // dE_r/dn_r = w_dec  (node_decoder, :106)
     }
     for (int idx = tid; idx < R * 4; idx += kCT) c.sDX[idx] = 0.f;
     csync();
@@ -1028,43 +1139,49 @@ __device__ void backward_pass_tc(const ModelDev& M, Ctx2& c) {
                                   st + M.off[ST_M], st + M.off[ST_G2], W.g2a, W.g2b);
         c.post();
         c.mark(11);
-        // feed-forward backward: d act [rows][4H] TMEM -> shared once; times GELU'(pre) 64 columns at a time -> slot
-        c.d1_wait();
-        c.mark(8);
+        // feed-forward backward: d act TMEM -> shared, up to 256 columns at a time; times GELU'(pre) 64 columns at a time -> slot
         float* sH = c.sQKV;
-        tmem_foreach<256>(c.tmem, kColD, rows, [&](int row, int col, const float (&v)[16]) {
+        const int nch64 = (4 * H) / 64;
+        for (int c0 = 0; c0 < nch64; c0 += 4) {
+            const int nc = min(4, nch64 - c0);
+            c.d1_wait();
+            c.mark(8);
+            tmem_foreach<256>(c.tmem, C::kColD, rows, [&](int row, int col, const float (&v)[16]) {
 #pragma unroll
-            for (int i = 0; i < 16; i += 4)
-                *reinterpret_cast<float4*>(sH + row * kLDF + col + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-        });
-        tc::fence_before_sync();
-        csync();
-        c.mark(12);
-        for (int ch = 0; ch < 4; ++ch) {
-            constexpr int MG = (R * 16) / kCT;
-            float4 gq[MG];
+                for (int i = 0; i < 16; i += 4)
+                    *reinterpret_cast<float4*>(sH + row * kLDF + col + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            });
+            tc::fence_before_sync();
+            csync();
+            if (c0 + 4 < nch64) c.post();
+            c.mark(12);
+            for (int ch = 0; ch < nc; ++ch) {
+                constexpr int MG = (R * 16) / kCT;
+                const int gc = (c0 + ch) * 64;
+                float4 gq[MG];
 #pragma unroll
-            for (int g = 0; g < MG; ++g) {
-                const int idx = tid + g * kCT;
-                if (idx < rows * 16) {
-                    const int r = idx >> 4, k4 = idx & 15;
-                    const float4 p = *reinterpret_cast<const float4*>(st + M.off[ST_H1] + (size_t)r * (4 * H) + ch * 64 + k4 * 4);
-                    const float4 v = *reinterpret_cast<const float4*>(sH + r * kLDF + ch * 64 + k4 * 4);
-                    gq[g] = make_float4(v.x * gelu_grad_f(p.x), v.y * gelu_grad_f(p.y), v.z * gelu_grad_f(p.z), v.w * gelu_grad_f(p.w));
+                for (int g = 0; g < MG; ++g) {
+                    const int idx = tid + g * kCT;
+                    if (idx < rows * 16) {
+                        const int r = idx >> 4, k4 = idx & 15;
+                        const float4 p = *reinterpret_cast<const float4*>(st + M.off[ST_H1] + (size_t)r * (4 * H) + gc + k4 * 4);
+                        const float4 v = *reinterpret_cast<const float4*>(sH + r * kLDF + ch * 64 + k4 * 4);
+                        gq[g] = make_float4(v.x * gelu_grad_f(p.x), v.y * gelu_grad_f(p.y), v.z * gelu_grad_f(p.z), v.w * gelu_grad_f(p.w));
+                    }
                 }
-            }
-            c.slot_acquire();
+                c.slot_acquire();
 #pragma unroll
-            for (int g = 0; g < MG; ++g) {
-                const int idx = tid + g * kCT;
-                if (idx < rows * 16) can_store4(c.slot_hi, c.slot_lo, idx >> 4, idx & 15, gq[g]);
+                for (int g = 0; g < MG; ++g) {
+                    const int idx = tid + g * kCT;
+                    if (idx < rows * 16) can_store4(c.slot_hi, c.slot_lo, idx >> 4, idx & 15, gq[g]);
+                }
+                c.slot_post();
             }
-            c.slot_post();
         }
         c.mark(13);
         c.acc_wait();
         c.mark(5);
-        tmem_foreach<64>(c.tmem, kColAcc, rows, [&](int row, int col, const float (&v)[16]) {
+        tmem_foreach<C::kHP>(c.tmem, kColAcc, rows, [&](int row, int col, const float (&v)[16]) {
 #pragma unroll
             for (int i = 0; i < 16; i += 4)
                 *reinterpret_cast<float4*>(c.sNh + row * C::LDH + col + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
@@ -1092,7 +1209,7 @@ __device__ void backward_pass_tc(const ModelDev& M, Ctx2& c) {
                 c.mark(15);
                 const int b = c.dq_wait();
                 c.mark(1);
-                tmem_foreach<64>(c.tmem, kColD + b * 64, rows, [&](int row, int col, const float (&v)[16]) {
+                tmem_foreach<64>(c.tmem, C::kColD + b * 64, rows, [&](int row, int col, const float (&v)[16]) {
 #pragma unroll
                     for (int i = 0; i < 16; i += 4)
                         *reinterpret_cast<float4*>(c.sO + row * C::LDO + col + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
@@ -1112,7 +1229,7 @@ __device__ void backward_pass_tc(const ModelDev& M, Ctx2& c) {
         }
         if (l > 0) {
             c.acc_wait();
-            tmem_foreach<64>(c.tmem, kColAcc, rows, [&](int row, int col, const float (&v)[16]) {
+            tmem_foreach<C::kHP>(c.tmem, kColAcc, rows, [&](int row, int col, const float (&v)[16]) {
 #pragma unroll
                 for (int i = 0; i < 16; i += 4)
                     *reinterpret_cast<float4*>(c.sNh + row * C::LDH + col + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
@@ -1149,7 +1266,7 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
 
     for (int idx = tid; idx < C::oW; idx += kTcThreads) smem[idx] = 0.f;             // activations, operands
     for (int idx = C::oX + tid; idx < C::oJobs; idx += kTcThreads) smem[idx] = 0.f;
-    for (int idx = tid; idx < njobs * 8; idx += kTcThreads)
+    for (int idx = tid; idx < njobs * 4; idx += kTcThreads)
         reinterpret_cast<uint32_t*>(jobs)[idx] = reinterpret_cast<const uint32_t*>(T.jobs)[idx];
     if (tid == 0) {
         for (int i = 0; i < kTcStages; ++i) { mbar_init(bars + B_FULL + i, 1); mbar_init(bars + B_EMPTY + i, 1); }
@@ -1173,12 +1290,13 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
             for (uint32_t rep = 0; rep < reps; ++rep)
                 for (int j = 0; j < njobs; ++j) {
                     const TcJob jb = jobs[j];
-                    const char* src = reinterpret_cast<const char*>(jb.base);
+                    const char* src = reinterpret_cast<const char*>(T.wbase + jb.w_off);
+                    const uint32_t slice_bytes = (uint32_t)jb.slice_16b * 16u;
                     for (uint32_t s = 0; s < jb.n_slices; ++s, ++slice_i) {
                         const uint32_t stg = slice_i % kTcStages, use = slice_i / kTcStages;
                         { TCP_BEGIN(); if (use > 0) mbar_wait_wd(bars + B_EMPTY + stg, (use - 1) & 1u, 5); TCP_END(pw, 0); }
-                        mbar_expect_tx(bars + B_FULL + stg, jb.slice_bytes);
-                        bulk_g2s(smem + C::oW + stg * kTcStageFloats, src + (size_t)s * jb.slice_bytes, jb.slice_bytes, bars + B_FULL + stg);
+                        mbar_expect_tx(bars + B_FULL + stg, slice_bytes);
+                        bulk_g2s(smem + C::oW + stg * C::kStageFloats, src + (size_t)s * slice_bytes, slice_bytes, bars + B_FULL + stg);
                     }
                 }
             (void)nslices;
@@ -1204,13 +1322,13 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
             for (uint32_t rep = 0; rep < reps; ++rep)
                 for (int j = 0; j < njobs; ++j) {
                     // job fields, made warp-uniform
-                    const uint32_t* jw = reinterpret_cast<const uint32_t*>(jobs + j);      // words 3..6 of the 32-byte entry
-                    const uint32_t f0 = __shfl_sync(0xffffffffu, jw[3], 0), f1 = __shfl_sync(0xffffffffu, jw[4], 0);
-                    const uint32_t f2 = __shfl_sync(0xffffffffu, jw[5], 0), f3 = __shfl_sync(0xffffffffu, jw[6], 0);
-                    const uint32_t n_slices = f0 & 0xffffu, ks = f0 >> 16, n = f1 & 0xffffu;
+                    const uint32_t* jw = reinterpret_cast<const uint32_t*>(jobs + j);      // words 1..3 of the 16-byte entry
+                    const uint32_t f0 = __shfl_sync(0xffffffffu, jw[1], 0), f1 = __shfl_sync(0xffffffffu, jw[2], 0);
+                    const uint32_t f2 = __shfl_sync(0xffffffffu, jw[3], 0);
+                    const uint32_t n_slices = (f0 >> 16) & 0xffu, ks = f0 >> 24, n = f1 & 0xffffu;
                     uint32_t dcol = f1 >> 16;
-                    const uint32_t a_slot = f2 & 0xffu, acc_first = (f2 >> 8) & 0xffu, wait_post = (f2 >> 16) & 0xffu, dbuf = f2 >> 24;
-                    const uint32_t commit_acc = f3 & 0xffu, commit_d1 = (f3 >> 8) & 0xffu;
+                    const uint32_t a_slot = f2 & TCJ_SLOT, acc_first = (f2 & TCJ_ACC) ? 1u : 0u, wait_post = f2 & TCJ_WAIT_POST, dbuf = f2 & TCJ_DBUF;
+                    const uint32_t commit_acc = f2 & TCJ_COMMIT_ACC, commit_d1 = f2 & TCJ_COMMIT_D1;
                     if (wait_post) {
                         ++post_seq;
                         TCP_BEGIN(); spin_until(ctr, post_seq, 7); TCP_END(iw, 0);
@@ -1231,7 +1349,7 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
                     uint32_t acc = acc_first;
                     for (uint32_t s = 0; s < n_slices; ++s, ++slice_i) {
                         const uint32_t stg = slice_i % kTcStages, use = slice_i / kTcStages;
-                        uint64_t dbh = descB | (uint64_t)(((ring_a + stg * (kTcStageFloats * 4)) >> 4) & 0x3FFFu);
+                        uint64_t dbh = descB | (uint64_t)(((ring_a + stg * (C::kStageFloats * 4)) >> 4) & 0x3FFFu);
                         uint64_t dbl = dbh + lo_off;
                         { TCP_BEGIN(); mbar_wait_wd(bars + B_FULL + stg, use & 1u, 6); TCP_END(iw, 2); }
                         tc::fence_after_sync();
@@ -1271,7 +1389,7 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
     } else {
         // ===================================================== compute warps
         Ctx2 c;
-        c.sN = smem + C::oN; c.sQKV = smem + C::oQKV; c.sNh = c.sQKV; c.sO = smem + C::oO;
+        c.sQKV = smem + C::oQKV; c.sNh = c.sQKV; c.sO = smem + C::oO;
         c.sP = smem + C::oP; c.sDS = smem + C::oDS; c.sX = smem + C::oX; c.sV = smem + C::oV;
         c.sDX = smem + C::oDX; c.sTmp = smem + C::oTmp;
         c.nhat_hi = smem + C::oNhatHi; c.nhat_lo = smem + C::oNhatLo; c.slot_hi = smem + C::oSlotHi; c.slot_lo = smem + C::oSlotLo;
@@ -1284,6 +1402,8 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
         c.last = t_begin;
 #endif
         c.stash = M.scratch + (size_t)blockIdx.x * M.scratch_per_cta;
+        // node stream [R][LDH]: shared memory for hidden 64, the tail of this CTA's global scratch otherwise
+        c.sN = C::kNodeInSmem ? smem + C::oN : c.stash + (M.scratch_per_cta - (long long)R * (128 + 4));
 
         uint32_t flags = 0;
         for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
