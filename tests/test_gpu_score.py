@@ -135,13 +135,17 @@ def test_tcgen05_and_mma_sync_kernels_agree(batch, monkeypatch):
     assert rel_err(out["tc"], out["legacy"]) < FORCE_RTOL
 
 
-def test_tcgen05_is_the_default_up_to_32_beads(monkeypatch):
-    """hidden 64 / 96 / 128 with N <= 32 run the tcgen05 kernel; protein G (56 beads) stays on the mma.sync kernel."""
+def test_tcgen05_is_the_default_for_every_shipped_protein(monkeypatch):
+    """hidden 64 / 96 / 128 up to 56 beads run the tcgen05 kernel; only N > 56 at hidden > 64 falls back to mma.sync."""
+    from oracle.weights import synthetic_net_params
     monkeypatch.delenv("DFF_CONFIG", raising=False)
-    for mol, n, want in (("chignolin", 10, "tc"), ("ala2_fold1", 5, "tc"), ("trp_cage", 20, "tc"), ("protein_g", 56, None)):
+    for mol, n in (("chignolin", 10), ("ala2_fold1", 5), ("trp_cage", 20), ("protein_g", 56)):
         eng = _engine(net_params(mol))
         eng.score(torch.zeros(2, n, 3, device="cuda"), 0.02)
-        assert (eng.last_config == want) if want else (eng.last_config in ("wide", "tall", "duo")), (mol, eng.last_config)
+        assert eng.last_config == "tc", (mol, eng.last_config)
+    eng = _engine(synthetic_net_params(64, 128, 2, 8))
+    eng.score(torch.zeros(1, 64, 3, device="cuda"), 0.02)
+    assert eng.last_config in ("wide", "tall", "duo")
 
 
 def test_nonconservative_head_vs_reference_golden():
@@ -190,7 +194,7 @@ def test_nonconservative_head_mma_sync_kernel(monkeypatch):
         assert eng.last_config != "tc" and rel_err(eps, c["forces"]) < FORCE_RTOL, (key, rel_err(eps, c["forces"]))
 
 
-@pytest.mark.parametrize("mol", ["ala2_fold1", "trp_cage"])
+@pytest.mark.parametrize("mol", ["ala2_fold1", "trp_cage", "protein_g"])
 def test_tcgen05_and_mma_sync_agree_hidden_96_128(mol, monkeypatch):
     from oracle import collapsed_ref, score_ref
     p = net_params(mol)

@@ -195,10 +195,12 @@ int launch(dff_model* m, StepArgs& A, cudaStream_t stream) {
         m->last_R = 64; m->last_S = S; m->last_cfg = "tc";
         if (m->HP == 64) {
             if (m->NP <= 12) return launch_tc<v2::TcCfg<12, 64>>(m, M, A, grid, stream);
-            return launch_tc<v2::TcCfg<32, 64>>(m, M, A, grid, stream);
+            if (m->NP <= 32) return launch_tc<v2::TcCfg<32, 64>>(m, M, A, grid, stream);
+            return launch_tc<v2::TcCfg<64, 64>>(m, M, A, grid, stream);
         }
         if (m->NP <= 12) return launch_tc<v2::TcCfg<12, 128>>(m, M, A, grid, stream);
-        return launch_tc<v2::TcCfg<32, 128>>(m, M, A, grid, stream);
+        if (m->NP <= 32) return launch_tc<v2::TcCfg<32, 128>>(m, M, A, grid, stream);
+        return launch_tc<v2::TcCfg<56, 128>>(m, M, A, grid, stream);
     }
     int R, S, ctas;
     ModelDev M;
@@ -400,7 +402,7 @@ int dff_model_create_ex(dff_model_t** out, int device, int num_beads, int hidden
     std::vector<TcJobHost> tcj;
     int tc_njobs_fwd = 0;
     uint32_t tc_nslice_fwd = 0, tc_nslice_all = 0;
-    const bool tc_shape = ((H == 64 || H == 96 || H == 128) && N <= 32);
+    const bool tc_shape = ((H == 64 && N <= 64) || ((H == 96 || H == 128) && N <= 56));   // shared-memory budget of TcCfg
     if (tc_shape) {
         const int stage_bytes = (HP == 64 ? 4096 : 3072) * 4;            // must equal TcCfg::kStageFloats
         auto job = [&](int K, int NN, auto&& fill /* (k, n) -> value */, int d_col, uint32_t flags) {

@@ -90,6 +90,7 @@ struct TcCfg {
     static constexpr int NHAT_CHUNKS = kHP / 4 + 2;          // + [x0 x1 x2 1] chunk + zero chunk (K = H + 8 for the QKV jobs)
     static constexpr int SLOT_CHUNKS = 16;
     static constexpr bool kNodeInSmem = (kHP == 64);
+    static constexpr int kStages = (PN_ > 32) ? 2 : 3;   // weight ring depth (N > 32 needs the room for p / ds)
     static constexpr int kStageFloats = (kHP == 64) ? 4096 : 3072;
     static constexpr uint32_t kColD = kHP;                   // TMEM work area
     // shared memory carve-up (float offsets)
@@ -103,7 +104,7 @@ struct TcCfg {
     static constexpr int oSlotHi = oNhatLo + NHAT_CHUNKS * kCS;   // canonical rotating A operand
     static constexpr int oSlotLo = oSlotHi + SLOT_CHUNKS * kCS;
     static constexpr int oW = oSlotLo + SLOT_CHUNKS * kCS;   // weight ring
-    static constexpr int oX = oW + kTcStages * kStageFloats;
+    static constexpr int oX = oW + kStages * kStageFloats;
     static constexpr int oV = oX + kR * 4;
     static constexpr int oDX = oV + kR * 4;
     static constexpr int oTmp = oDX + kR * 4;
@@ -486,6 +487,7 @@ struct AttnMap {
     static constexpr int LPR = (C::kPN <= 16) ? 16 : 32;
     static constexpr int DPL = 64 / LPR;
     static constexpr int UPW = 32 / LPR;              // rows per warp and round
+    static constexpr int KPL = (C::kPN > 32) ? 2 : 1; // keys per lane (N > 32: lane j also owns key j + 32; pair-local routines only)
 };
 template <int LPR>
 __device__ __forceinline__ float group_sum(float v) {
@@ -786,7 +788,7 @@ __device__ __forceinline__ void dot64x2(const float* __restrict__ a0, const floa
 template <class C>
 __device__ __forceinline__ void attn_forward_pairs(Ctx2& c, const LayerDev& W, int hc, int N, int NP, float* st_p) {
     using AM = AttnMap<C>;
-    constexpr int LPR = AM::LPR, DPL = AM::DPL, NG = kCW * AM::UPW;
+    constexpr int LPR = AM::LPR, DPL = AM::DPL, NG = kCW * AM::UPW, KPL = AM::KPL;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane % LPR, gbase = lane - sub, gid = warp * AM::UPW + lane / LPR;
     const int pps = (N + 1) >> 1, n_units = c.S_act * pps;
@@ -798,30 +800,54 @@ __device__ __forceinline__ void attn_forward_pairs(Ctx2& c, const LayerDev& W, i
         const float4 a4 = __ldg(reinterpret_cast<const float4*>(W.A + col * 4));
         ax[e][0] = a4.x; ax[e][1] = a4.y; ax[e][2] = a4.z;
     }
-    const bool act = sub < N;
     for (int base = 0; base < n_units; base += NG) {
         const PairUnit u = pair_unit<C>(base + gid, n_units, pps, N);
         const int ra = u.r0 + u.ia, rb = u.r0 + u.ib;
-        float da, db;
-        group_dots<LPR, DPL, true>(c.sQKV + ra * C::LDQ, c.sQKV + rb * C::LDQ, c.sQKV + u.r0 * C::LDQ + 64, C::LDQ, N, sub, da, db);
-        const float la = act ? kAttnScale * da : -INFINITY, lb = act ? kAttnScale * db : -INFINITY;
-        const float ma = group_max<LPR>(la), mb = group_max<LPR>(lb);
-        const float ea = act ? expf(la - ma) : 0.f, eb = act ? expf(lb - mb) : 0.f;
-        const float pa = ea / group_sum<LPR>(ea), pb = eb / group_sum<LPR>(eb);
-        if (u.valid && sub < NP) {
-            st_p[(size_t)ra * NP + sub] = pa;
-            if (u.has_b) st_p[(size_t)rb * NP + sub] = pb;
+        float la[KPL], lb[KPL];
+#pragma unroll
+        for (int kp = 0; kp < KPL; ++kp) {               // keys kp * LPR + sub
+            const int kb = kp * LPR, nk = min(LPR, N - kb);
+            float da, db;
+            group_dots<LPR, DPL, true>(c.sQKV + ra * C::LDQ, c.sQKV + rb * C::LDQ, c.sQKV + (u.r0 + kb) * C::LDQ + 64, C::LDQ, nk, sub, da, db);
+            const bool act = sub < nk;
+            la[kp] = act ? kAttnScale * da : -INFINITY;
+            lb[kp] = act ? kAttnScale * db : -INFINITY;
+        }
+        float ma = la[0], mb = lb[0];
+#pragma unroll
+        for (int kp = 1; kp < KPL; ++kp) { ma = fmaxf(ma, la[kp]); mb = fmaxf(mb, lb[kp]); }
+        ma = group_max<LPR>(ma); mb = group_max<LPR>(mb);
+        float pa[KPL], pb[KPL], sa = 0.f, sb = 0.f;
+#pragma unroll
+        for (int kp = 0; kp < KPL; ++kp) {
+            const bool act = kp * LPR + sub < N;
+            pa[kp] = act ? expf(la[kp] - ma) : 0.f; pb[kp] = act ? expf(lb[kp] - mb) : 0.f;
+            sa += pa[kp]; sb += pb[kp];
+        }
+        sa = group_sum<LPR>(sa); sb = group_sum<LPR>(sb);
+#pragma unroll
+        for (int kp = 0; kp < KPL; ++kp) {
+            pa[kp] = pa[kp] / sa; pb[kp] = pb[kp] / sb;
+            const int key = kp * LPR + sub;
+            if (u.valid && key < NP) {
+                st_p[(size_t)ra * NP + key] = pa[kp];
+                if (u.has_b) st_p[(size_t)rb * NP + key] = pb[kp];
+            }
         }
         float oa[DPL], ob[DPL];
 #pragma unroll
         for (int e = 0; e < DPL; ++e) { oa[e] = 0.f; ob[e] = 0.f; }
-        const float* vs = c.sQKV + u.r0 * C::LDQ + 128 + sub * DPL;
-        for (int j = 0; j < N; ++j) {
-            float v[DPL];
-            load_cols<LPR, DPL>(v, vs + j * C::LDQ);
-            const float wa = __shfl_sync(0xffffffffu, pa, gbase + j), wb = __shfl_sync(0xffffffffu, pb, gbase + j);
 #pragma unroll
-            for (int e = 0; e < DPL; ++e) { oa[e] = fmaf(wa, v[e], oa[e]); ob[e] = fmaf(wb, v[e], ob[e]); }
+        for (int kp = 0; kp < KPL; ++kp) {
+            const int kb = kp * LPR, nk = min(LPR, N - kb);
+            const float* vs = c.sQKV + (u.r0 + kb) * C::LDQ + 128 + sub * DPL;
+            for (int j = 0; j < nk; ++j) {
+                float v[DPL];
+                load_cols<LPR, DPL>(v, vs + j * C::LDQ);
+                const float wa = __shfl_sync(0xffffffffu, pa[kp], gbase + j), wb = __shfl_sync(0xffffffffu, pb[kp], gbase + j);
+#pragma unroll
+                for (int e = 0; e < DPL; ++e) { oa[e] = fmaf(wa, v[e], oa[e]); ob[e] = fmaf(wb, v[e], ob[e]); }
+            }
         }
         {
             const float x0 = c.sX[ra * 4], x1 = c.sX[ra * 4 + 1], x2 = c.sX[ra * 4 + 2];
@@ -843,33 +869,49 @@ __device__ __forceinline__ void attn_forward_pairs(Ctx2& c, const LayerDev& W, i
 template <class C>
 __device__ __forceinline__ void attn_backward_ds_dq_pairs(Ctx2& c, int N, int NP, bool want_dq) {
     using AM = AttnMap<C>;
-    constexpr int LPR = AM::LPR, DPL = AM::DPL, NG = kCW * AM::UPW;
+    constexpr int LPR = AM::LPR, DPL = AM::DPL, NG = kCW * AM::UPW, KPL = AM::KPL;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane % LPR, gbase = lane - sub, gid = warp * AM::UPW + lane / LPR;
     const int pps = (N + 1) >> 1, n_units = c.S_act * pps;
-    const bool act = sub < N;
     for (int base = 0; base < n_units; base += NG) {
         const PairUnit u = pair_unit<C>(base + gid, n_units, pps, N);
         const int ra = u.r0 + u.ia, rb = u.r0 + u.ib;
-        float dpa, dpb;
-        group_dots<LPR, DPL, true>(c.sO + ra * C::LDO, c.sO + rb * C::LDO, c.sQKV + u.r0 * C::LDQ + 128, C::LDQ, N, sub, dpa, dpb);
-        const float pa = act ? c.sP[ra * NP + sub] : 0.f, pb = act ? c.sP[rb * NP + sub] : 0.f;
-        const float dsa = pa * (dpa - group_sum<LPR>(pa * dpa)), dsb = pb * (dpb - group_sum<LPR>(pb * dpb));
-        if (u.valid && sub < NP) {
-            c.sDS[ra * NP + sub] = dsa;
-            if (u.has_b) c.sDS[rb * NP + sub] = dsb;
+        float pa[KPL], pb[KPL], dpa[KPL], dpb[KPL], ta = 0.f, tb = 0.f;
+#pragma unroll
+        for (int kp = 0; kp < KPL; ++kp) {
+            const int kb = kp * LPR, nk = min(LPR, N - kb);
+            group_dots<LPR, DPL, true>(c.sO + ra * C::LDO, c.sO + rb * C::LDO, c.sQKV + (u.r0 + kb) * C::LDQ + 128, C::LDQ, nk, sub, dpa[kp], dpb[kp]);
+            const bool act = sub < nk;
+            pa[kp] = act ? c.sP[ra * NP + kb + sub] : 0.f;
+            pb[kp] = act ? c.sP[rb * NP + kb + sub] : 0.f;
+            ta += pa[kp] * dpa[kp]; tb += pb[kp] * dpb[kp];
+        }
+        ta = group_sum<LPR>(ta); tb = group_sum<LPR>(tb);
+        float dsa[KPL], dsb[KPL];
+#pragma unroll
+        for (int kp = 0; kp < KPL; ++kp) {
+            dsa[kp] = pa[kp] * (dpa[kp] - ta); dsb[kp] = pb[kp] * (dpb[kp] - tb);
+            const int key = kp * LPR + sub;
+            if (u.valid && key < NP) {
+                c.sDS[ra * NP + key] = dsa[kp];
+                if (u.has_b) c.sDS[rb * NP + key] = dsb[kp];
+            }
         }
         if (want_dq) {
             float qa[DPL], qb[DPL];
 #pragma unroll
             for (int e = 0; e < DPL; ++e) { qa[e] = 0.f; qb[e] = 0.f; }
-            const float* ks = c.sQKV + u.r0 * C::LDQ + 64 + sub * DPL;
-            for (int j = 0; j < N; ++j) {
-                float v[DPL];
-                load_cols<LPR, DPL>(v, ks + j * C::LDQ);
-                const float wa = __shfl_sync(0xffffffffu, dsa, gbase + j), wb = __shfl_sync(0xffffffffu, dsb, gbase + j);
 #pragma unroll
-                for (int e = 0; e < DPL; ++e) { qa[e] = fmaf(wa, v[e], qa[e]); qb[e] = fmaf(wb, v[e], qb[e]); }
+            for (int kp = 0; kp < KPL; ++kp) {
+                const int kb = kp * LPR, nk = min(LPR, N - kb);
+                const float* ks = c.sQKV + (u.r0 + kb) * C::LDQ + 64 + sub * DPL;
+                for (int j = 0; j < nk; ++j) {
+                    float v[DPL];
+                    load_cols<LPR, DPL>(v, ks + j * C::LDQ);
+                    const float wa = __shfl_sync(0xffffffffu, dsa[kp], gbase + j), wb = __shfl_sync(0xffffffffu, dsb[kp], gbase + j);
+#pragma unroll
+                    for (int e = 0; e < DPL; ++e) { qa[e] = fmaf(wa, v[e], qa[e]); qb[e] = fmaf(wb, v[e], qb[e]); }
+                }
             }
 #pragma unroll
             for (int e = 0; e < DPL; ++e) { qa[e] *= kAttnScale; qb[e] *= kAttnScale; }
@@ -1269,7 +1311,7 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
     for (int idx = tid; idx < njobs * 4; idx += kTcThreads)
         reinterpret_cast<uint32_t*>(jobs)[idx] = reinterpret_cast<const uint32_t*>(T.jobs)[idx];
     if (tid == 0) {
-        for (int i = 0; i < kTcStages; ++i) { mbar_init(bars + B_FULL + i, 1); mbar_init(bars + B_EMPTY + i, 1); }
+        for (int i = 0; i < C::kStages; ++i) { mbar_init(bars + B_FULL + i, 1); mbar_init(bars + B_EMPTY + i, 1); }
         mbar_init(bars + B_DQ, 1); mbar_init(bars + B_DQ + 1, 1);
         mbar_init(bars + B_ACC, 1); mbar_init(bars + B_D1, 1); mbar_init(bars + B_SLOT, 1);
         ctr[0] = 0; ctr[1] = 0;
@@ -1293,7 +1335,7 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
                     const char* src = reinterpret_cast<const char*>(T.wbase + jb.w_off);
                     const uint32_t slice_bytes = (uint32_t)jb.slice_16b * 16u;
                     for (uint32_t s = 0; s < jb.n_slices; ++s, ++slice_i) {
-                        const uint32_t stg = slice_i % kTcStages, use = slice_i / kTcStages;
+                        const uint32_t stg = slice_i % C::kStages, use = slice_i / C::kStages;
                         { TCP_BEGIN(); if (use > 0) mbar_wait_wd(bars + B_EMPTY + stg, (use - 1) & 1u, 5); TCP_END(pw, 0); }
                         mbar_expect_tx(bars + B_FULL + stg, slice_bytes);
                         bulk_g2s(smem + C::oW + stg * C::kStageFloats, src + (size_t)s * slice_bytes, slice_bytes, bars + B_FULL + stg);
@@ -1348,7 +1390,7 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
                     const uint32_t ksteps = ks >> 3;
                     uint32_t acc = acc_first;
                     for (uint32_t s = 0; s < n_slices; ++s, ++slice_i) {
-                        const uint32_t stg = slice_i % kTcStages, use = slice_i / kTcStages;
+                        const uint32_t stg = slice_i % C::kStages, use = slice_i / C::kStages;
                         uint64_t dbh = descB | (uint64_t)(((ring_a + stg * (C::kStageFloats * 4)) >> 4) & 0x3FFFu);
                         uint64_t dbl = dbh + lo_off;
                         { TCP_BEGIN(); mbar_wait_wd(bars + B_FULL + stg, use & 1u, 6); TCP_END(iw, 2); }
