@@ -9,16 +9,17 @@
 //   * fp32-grade accuracy = 3xTF32 split precision: activations are written by their producers directly in the
 //     UMMA canonical K-major layout as a TF32-exact high part and a low part, the weights are pre-split on the
 //     host; lo*hi + hi*lo + hi*hi accumulate in the fp32 TMEM accumulator;
-//   * weights arrive as pre-split, pre-laid-out [hi | lo] slices through a 3-stage ring filled by a dedicated
+//   * weights arrive as pre-split, pre-laid-out [hi | lo] slices through a 2/3-stage ring filled by a dedicated
 //     TMA producer thread (cp.async.bulk + mbarrier expect_tx) and released by `tcgen05.commit`;
-//   * the CTA is warp-specialised: 8 compute warps (attention, softmax, LayerNorm, gates, GELU, integrators,
+//   * the CTA is warp-specialised: 16 compute warps (attention, softmax, LayerNorm, gates, GELU, integrators,
 //     TMEM epilogues) + 1 TMA producer warp + 1 MMA issuer warp.  The issuer follows a host-built job table, so
 //     the QKV projection of head chunk h+1 and the out-projection of chunk h-1 run on the tensor core WHILE the
 //     compute warps do the attention of chunk h (double-buffered TMEM accumulators);
 //   * the folded edge term  A x_j  and the q/k/v biases ride inside the QKV GEMM as 8 extra K rows
 //     (operand row = [n_hat | x0 x1 x2 1 0 0 0 0]), so that epilogue is a pure TMEM -> smem/stash copy.
 //
-// Shape support: hidden = 64 (chignolin-class nets), N <= PN beads.  Other shapes use dff_kernel.cuh.
+// Shape support (TcCfg<PN, HP>): hidden 64 with N <= 64 beads, hidden 96 / 128 with N <= 56 -- every shipped checkpoint.
+// Other shapes use dff_kernel.cuh.
 // Reference lines replaced: the same as dff_kernel.cuh (models/graph_transformer.py:87-111,143-159,178-329;
 // models/ddpm.py:195-251; dynamics/langevin.py:75-92; dynamics/langevin_cgnet.py:447-542,737-771).
 #pragma once
@@ -501,15 +502,6 @@ __device__ __forceinline__ float group_max(float v) {
     for (int o = LPR / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
-__device__ __forceinline__ float dot64(const float* __restrict__ a, const float* __restrict__ b) {
-    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-#pragma unroll
-    for (int t = 0; t < 16; ++t) {
-        const float4 x = *reinterpret_cast<const float4*>(a + 4 * t), y = *reinterpret_cast<const float4*>(b + 4 * t);
-        d0 = fmaf(x.x, y.x, d0); d1 = fmaf(x.y, y.y, d1); d2 = fmaf(x.z, y.z, d2); d3 = fmaf(x.w, y.w, d3);
-    }
-    return (d0 + d1) + (d2 + d3);
-}
 // dots of one (or two) shared-memory rows a (a2) with the N rows b_j of the sample, for all j at once:
 // every lane takes the DPL columns it owns, forms the partial products for every key j and the partials are then
 // summed across the group by a transpose-reduce (LPR - 1 shuffles), after which lane j holds  a . b_j.
@@ -769,20 +761,6 @@ __device__ __forceinline__ void load_cols(float (&v)[DPL], const float* __restri
         const float2 t = *reinterpret_cast<const float2*>(src);
         v[0] = t.x; v[1] = t.y;
     }
-}
-// two 64-long dot products against the same (register-free) streamed row b: a0 . b, a1 . b
-__device__ __forceinline__ void dot64x2(const float* __restrict__ a0, const float* __restrict__ a1, const float* __restrict__ b,
-                                        float& r0, float& r1) {
-    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f, e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
-#pragma unroll
-    for (int t = 0; t < 16; ++t) {
-        const float4 y = *reinterpret_cast<const float4*>(b + 4 * t);
-        const float4 x = *reinterpret_cast<const float4*>(a0 + 4 * t), z = *reinterpret_cast<const float4*>(a1 + 4 * t);
-        d0 = fmaf(x.x, y.x, d0); d1 = fmaf(x.y, y.y, d1); d2 = fmaf(x.z, y.z, d2); d3 = fmaf(x.w, y.w, d3);
-        e0 = fmaf(z.x, y.x, e0); e1 = fmaf(z.y, y.y, e1); e2 = fmaf(z.z, y.z, e2); e3 = fmaf(z.w, y.w, e3);
-    }
-    r0 = (d0 + d1) + (d2 + d3);
-    r1 = (e0 + e1) + (e2 + e3);
 }
 
 template <class C>
