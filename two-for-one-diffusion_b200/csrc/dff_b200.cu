@@ -190,7 +190,7 @@ int launch(dff_model* m, StepArgs& A, cudaStream_t stream) {
         const int n_groups = (A.B + S - 1) / S;
         const int grid = std::min(n_groups, m->num_sms);
         if (grid > m->scratch_ctas) return fail(DFF_EINVAL, "internal: grid %d exceeds scratch slots %d", grid, m->scratch_ctas);
-        const double slices = (double)((n_groups + grid - 1) / grid) * (double)A.n_steps * (double)m->tc.nslice_all;
+        const double slices = (double)((A.B / grid + 1 + S - 1) / S) * (double)A.n_steps * (double)m->tc.nslice_all;   // passes of the fullest CTA
         if (slices >= 4.0e9) return fail(DFF_EINVAL, "n_steps %d too large for one launch; split the call (e.g. per save interval)", A.n_steps);
         m->last_R = 64; m->last_S = S; m->last_cfg = "tc";
         if (m->HP == 64) {

@@ -1279,9 +1279,13 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
     const int njobs = A.need_backward ? T.njobs_all : T.njobs_fwd;
     const uint32_t nslices = A.need_backward ? T.nslice_all : T.nslice_fwd;
 
-    const int n_groups = (A.B + M.S - 1) / M.S;
-    int my_groups = 0;
-    for (int g = blockIdx.x; g < n_groups; g += gridDim.x) ++my_groups;
+    // Balanced work split: this CTA owns a contiguous range of samples (B / grid, +1 for the first B % grid CTAs) and
+    // walks it in the fewest passes of <= M.S samples, of near-equal size (e.g. 7 samples = 3 + 2 + 2, not 3 + 3 + 1):
+    // a pass costs roughly in proportion to its rows, so equal passes and equal ranges minimise the makespan.
+    const int per = A.B / (int)gridDim.x, rem = A.B % (int)gridDim.x;
+    const int my_n = per + ((int)blockIdx.x < rem ? 1 : 0);
+    const int my_start = (int)blockIdx.x * per + min((int)blockIdx.x, rem);
+    const int my_groups = (my_n + M.S - 1) / M.S;
     const uint32_t reps = (uint32_t)my_groups * (uint32_t)A.n_steps;
 
     for (int idx = tid; idx < C::oW; idx += kTcThreads) smem[idx] = 0.f;             // activations, operands
@@ -1426,9 +1430,11 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
         c.sN = C::kNodeInSmem ? smem + C::oN : c.stash + (M.scratch_per_cta - (long long)R * (128 + 4));
 
         uint32_t flags = 0;
-        for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
-            const int s0 = g * M.S;
-            c.S_act = min(M.S, A.B - s0);
+        int s_next = my_start;
+        for (int g = 0; g < my_groups; ++g) {
+            const int s0 = s_next;
+            c.S_act = my_n / my_groups + (g < my_n % my_groups ? 1 : 0);
+            s_next += c.S_act;
             c.rows_act = c.S_act * N;
 #ifdef DFF_TC_PAIRS_ALWAYS
             c.pairs = true;
