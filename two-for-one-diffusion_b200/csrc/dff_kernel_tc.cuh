@@ -1036,13 +1036,16 @@ __device__ void forward_pass_tc(const ModelDev& M, Ctx2& c, float t_norm) {
                 float* st_qkv = st + M.off[ST_QKV] + (size_t)hc * R * 3 * C::CWQ;
                 tmem_foreach<192>(c.tmem, C::kColD + b * 192, rows, [&](int row, int col, const float (&v)[16]) {
 #pragma unroll
-                    for (int i = 0; i < 16; i += 4) {
-                        const float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                        *reinterpret_cast<float4*>(c.sQKV + row * C::LDQ + col + i) = o;
-                        *reinterpret_cast<float4*>(st_qkv + (size_t)row * (3 * C::CWQ) + col + i) = o;
-                    }
+                    for (int i = 0; i < 16; i += 4)
+                        *reinterpret_cast<float4*>(c.sQKV + row * C::LDQ + col + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
                 });
                 c.dq_release();
+                // stash copy for the reverse pass: coalesced row stores by all threads, issued after the hand-off so that
+                // they drain during the attention phase (no fence waits on them)
+                for (int idx = tid; idx < rows * 48; idx += kCT) {
+                    const int r = idx / 48, c4 = idx - r * 48;
+                    *reinterpret_cast<float4*>(st_qkv + (size_t)r * (3 * C::CWQ) + c4 * 4) = *reinterpret_cast<const float4*>(c.sQKV + r * C::LDQ + c4 * 4);
+                }
                 c.mark(2);
             }
             // logits, softmax, P V' - A x_i + c -> canonical operand of the out-projection (row-local, no barrier inside)
