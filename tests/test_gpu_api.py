@@ -159,3 +159,43 @@ def test_distribution_matches_reference_samples():
             assert float(((d.std(0) / r["std"]) - 1).abs().max()) < 0.25, (mol, rng)
             h = torch.histc(d.flatten(), bins=60, min=0.0, max=r["hi"])
             assert sampler_ref.js_divergence(h.numpy(), r["hist"].numpy()) < 5e-3, (mol, rng)
+
+
+def _langevin(ddpm, init, length, si, rng, seed, friction=1.0, **kw):
+    """A bare dynamics.langevin_cgnet.Langevin on the chignolin force field (the object LangevinDiffusion builds)."""
+    from dynamics.langevin import ForcesWrapper
+    from dynamics.langevin_cgnet import Langevin
+    fw = ForcesWrapper(ddpm, 20, 1000, kbt_inv=0.0343).eval()
+    return Langevin(fw, init.clone(), length=length, save_interval=si, beta=0.0343, masses=[12.0] * 10, friction=friction,
+                    dt=7.7e-4, device=torch.device("cuda"), rng=rng, random_seed=seed, **kw)
+
+
+@pytest.mark.parametrize("rng", ["torch", "philox"])
+def test_langevin_npy_export_log_and_restart(tmp_path, rng):
+    """npy chunk export + file log with the reference's names (langevin_cgnet.py:544-603), and an MD
+    restart in a fresh integrator (state_dict / load_state_dict) that continues the trajectory bit for bit."""
+    import numpy as np
+    ddpm = _ddpm("chignolin", rng=rng)
+    init = load("langevin_chignolin.pt")["runs"][0]["init_mol"] / load("score_chignolin.pt")["meta"]["std"]
+    B = init.shape[0]
+    base = str(tmp_path / "run")
+    sim = _langevin(ddpm, init, 60, 10, rng, 7, export_interval=20, filename=base, log_interval=20, log_type="write")
+    coords = sim.simulate()                                       # [B, 6 frames, 10, 3]
+    assert coords.shape == (B, 6, 10, 3)
+    for k in range(3):
+        part = np.load(f"{base}_coords_{k:03d}.npy")
+        ke = np.load(f"{base}_kineticenergy_{k:03d}.npy")
+        assert np.array_equal(part, coords[:, 2 * k:2 * k + 2]) and np.array_equal(ke, sim.kinetic_energies[:, 2 * k:2 * k + 2])
+    log = open(base + "_log.txt").read().splitlines()
+    assert [l.split(" time")[0] for l in log if "time points" in l] == ["2/6", "4/6", "6/6"]
+    with pytest.raises(ValueError):                                # refuses to overwrite, like the reference
+        _langevin(ddpm, init, 60, 10, rng, 7, export_interval=20, filename=base)
+    # restart: 30 steps, save, continue in a new object == 60 steps in one go
+    a = _langevin(ddpm, init, 60, 10, rng, 7)
+    a.simulate(sub_interval=30)
+    state = a.state_dict()
+    torch.save(state, tmp_path / "restart.pt")
+    b = _langevin(ddpm, init, 60, 10, rng, 99)
+    b.load_state_dict(torch.load(tmp_path / "restart.pt", weights_only=False))
+    tail = b.simulate(sub_interval=30)
+    assert b.t == 60 and np.array_equal(tail, coords[:, 3:])
