@@ -159,6 +159,20 @@ int dff_langevin_run_host(dff_model_t* m, float* x_host, float* v_host, int batc
                           const dff_md_params_t* prm, const float* mass_host, uint64_t seed,
                           int save_interval, float* frames_host, float* ke_host, uint32_t* flags_host);
 
+/* == Pairwise-distance statistics of sampled structures, the arithmetic of
+ *    get_pwd_triu_batch (evaluate/evaluators.py:934-948) + the torch.histc loops of PwdEvaluator (:241-263).
+ * Pairs are ordered like torch.triu_indices(N, N, offset): (i, j) with j - i >= offset, row-major.
+ * x_dev [n, N, 3] fp32 (any units).  No model handle is needed.
+ *   dff_pwd_num_pairs : number of pairs P
+ *   dff_pwd_max_dev   : max_out_dev [P] (zero-initialised by the caller) = per-pair maximum distance over the n structures
+ *   dff_pwd_hist_dev  : hist_dev [P, ld_hist] uint32 (zero-initialised by the caller) += histogram of pair p with
+ *                       nbins_dev[p] <= ld_hist equal-width bins over [0, resolution * nbins[p]] (torch.histc semantics:
+ *                       out-of-range values are ignored, the upper edge falls in the last bin). */
+int dff_pwd_num_pairs(int num_beads, int offset);
+int dff_pwd_max_dev(const float* x_dev, int n, int num_beads, int offset, float* max_out_dev, void* stream);
+int dff_pwd_hist_dev(const float* x_dev, int n, int num_beads, int offset, float resolution, const int* nbins_dev,
+                     int ld_hist, uint32_t* hist_dev, void* stream);
+
 /* Test hook: after a dff_score_* call with batch <= samples-per-CTA-group, copies the first CTA's
  * activation stash (the per-layer intermediates kept for the backward pass) to host.
  * Returns the number of floats written (<= cap) or a negative error. */

@@ -100,3 +100,13 @@ def test_nonconservative_head_matches_reference():
         p = synthetic_net_params(c["N"], c["H"], c["L"], c["seed"], out_dim=3)
         f = score_ref.score_forward(p, c["x"], c["t_norm"])
         assert f.shape == c["forces"].shape and rel_err(f, c["forces"]) < 2e-6, (key, rel_err(f, c["forces"]))
+
+
+def test_pwd_metric_oracle_matches_reference():
+    """PwdEvaluator restatement (oracle/metrics_ref.py) == the reference's own PwdEvaluator.eval on the golden structures
+    (tests/golden/pwd_metric.pt, made by oracle/make_golden_metrics.py) against the reference's saved MD histograms."""
+    from oracle import metrics_ref
+    g, r = load("pwd_metric.pt"), load("pwd_ref_chignolin.pt")
+    mx, hists = metrics_ref.pwd_histograms(g["x"], r["gt_max"], g["offset"], g["resolution"])
+    assert torch.equal(mx, g["pwd_max"]) and all(torch.equal(a, b) for a, b in zip(hists, g["hists"]))
+    assert metrics_ref.pwd_js(g["x"], r["gt_hist"], r["gt_max"], g["offset"], g["resolution"]) == g["js"]

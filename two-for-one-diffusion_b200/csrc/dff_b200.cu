@@ -14,6 +14,7 @@
 #include "dff_kernel.cuh"
 #include "dff_tc.cuh"
 #include "dff_kernel_tc.cuh"
+#include "dff_metrics.cuh"
 
 using namespace dff;
 
@@ -704,6 +705,38 @@ int dff_langevin_run_host(dff_model_t* m, float* x_host, float* v_host, int batc
     if (ke_host && nf) CUDA_TRY(cudaMemcpyAsync(ke_host, m->d_io[4], nf * batch * sizeof(float), cudaMemcpyDeviceToHost, 0));
     if (flags_host) CUDA_TRY(cudaMemcpyAsync(flags_host, m->d_flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, 0));
     CUDA_TRY(cudaStreamSynchronize(0));
+    return DFF_OK;
+}
+
+int dff_pwd_num_pairs(int num_beads, int offset) {
+    int p = 0;
+    for (int i = 0; i < num_beads; ++i) p += std::max(0, num_beads - offset - i);
+    return p;
+}
+
+int dff_pwd_max_dev(const float* x_dev, int n, int num_beads, int offset, float* max_out_dev, void* stream) {
+    if (!x_dev || !max_out_dev) return fail(DFF_EINVAL, "NULL argument");
+    const int P = dff_pwd_num_pairs(num_beads, offset);
+    if (n <= 0 || P <= 0) return DFF_OK;
+    if (P > 12000) return fail(DFF_EINVAL, "too many bead pairs (%d) for the shared-memory reduction", P);
+    const long long total = (long long)n * P;
+    const int grid = (int)std::min<long long>((total + 255) / 256, 148LL * 8);
+    dff_pwd_max_kernel<<<grid, 256, (size_t)P * sizeof(unsigned int), (cudaStream_t)stream>>>(
+        x_dev, n, num_beads, offset, P, reinterpret_cast<unsigned int*>(max_out_dev));
+    CUDA_TRY(cudaGetLastError());
+    return DFF_OK;
+}
+
+int dff_pwd_hist_dev(const float* x_dev, int n, int num_beads, int offset, float resolution, const int* nbins_dev,
+                     int ld_hist, uint32_t* hist_dev, void* stream) {
+    if (!x_dev || !nbins_dev || !hist_dev) return fail(DFF_EINVAL, "NULL argument");
+    if (!(resolution > 0.f) || ld_hist <= 0) return fail(DFF_EINVAL, "resolution and ld_hist must be positive");
+    const int P = dff_pwd_num_pairs(num_beads, offset);
+    if (n <= 0 || P <= 0) return DFF_OK;
+    const long long total = (long long)n * P;
+    const int grid = (int)std::min<long long>((total + 255) / 256, 148LL * 8);
+    dff_pwd_hist_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x_dev, n, num_beads, offset, P, resolution, nbins_dev, ld_hist, hist_dev);
+    CUDA_TRY(cudaGetLastError());
     return DFF_OK;
 }
 

@@ -50,6 +50,9 @@ SYMBOLS = {
     "dff_ddpm_sample_host": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.POINTER(_vp), C.c_uint64, _vp]),
     "dff_langevin_run_host": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.POINTER(MdParams), _vp, C.c_uint64, C.c_int,
                                         _vp, _vp, _vp]),
+    "dff_pwd_num_pairs": (C.c_int, [C.c_int, C.c_int]),
+    "dff_pwd_max_dev": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "dff_pwd_hist_dev": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_float, _vp, C.c_int, _vp, _vp]),
     "dff_debug_read_stash": (C.c_int64, [_vp, _vp, C.c_int64]),
     "dff_debug_tc_gemm": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     "dff_debug_stash_layout": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
