@@ -489,12 +489,15 @@ int dff_model_create_ex(dff_model_t** out, int device, int num_beads, int hidden
             jdo(0, TCJ_WAIT_POST); jdo(1, 0);
             for (int hc = 0; hc < 8; ++hc) {
                 if (l > 0) {
+                    // d n_hat = dq Wq + dk' Wk + dv' Wv accumulates over the 8 head chunks in THREE TMEM accumulators (one per
+                    // product) that the epilogue adds in fp32: the tensor core's accumulation chain is 192 MMAs long instead of
+                    // 576 (its accumulate rounding is what separates this kernel's error from the reference's own)
                     job(64, HP, [&](int j, int d) -> float { return d < H ? Wq[(size_t)(hc * 64 + j) * H + d] : 0.f; }, cA,
                         TCJ_SLOT | TCJ_WAIT_POST | (hc > 0 ? TCJ_ACC : 0));
-                    job(64, HP, [&](int j, int d) -> float { return d < H ? Wkv[(size_t)(hc * 64 + j) * H + d] : 0.f; }, cA,
-                        TCJ_SLOT | TCJ_WAIT_POST | TCJ_ACC);
-                    job(64, HP, [&](int j, int d) -> float { return d < H ? Wkv[(size_t)(512 + hc * 64 + j) * H + d] : 0.f; }, cA,
-                        TCJ_SLOT | TCJ_WAIT_POST | TCJ_ACC | (hc == 7 ? TCJ_COMMIT_ACC : 0));
+                    job(64, HP, [&](int j, int d) -> float { return d < H ? Wkv[(size_t)(hc * 64 + j) * H + d] : 0.f; }, cD + 128,
+                        TCJ_SLOT | TCJ_WAIT_POST | (hc > 0 ? TCJ_ACC : 0));
+                    job(64, HP, [&](int j, int d) -> float { return d < H ? Wkv[(size_t)(512 + hc * 64 + j) * H + d] : 0.f; }, cD + 128 + HP,
+                        TCJ_SLOT | TCJ_WAIT_POST | (hc > 0 ? TCJ_ACC : 0) | (hc == 7 ? TCJ_COMMIT_ACC : 0));
                 }
                 if (hc + 2 < 8) jdo(hc + 2, 0);
             }

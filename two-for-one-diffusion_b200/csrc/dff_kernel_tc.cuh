@@ -116,7 +116,7 @@ struct TcCfg {
     static_assert(kR * LDH <= kR * LDQ, "row buffer must fit the q|k'|v' buffer");
     static_assert(oNhatHi % 4 == 0 && oSlotHi % 4 == 0 && oW % 4 == 0 && oJobs % 4 == 0 && oBar % 4 == 0, "16-byte alignment");
     static_assert(kSmemBytes <= 232448, "exceeds the 227 KB dynamic shared memory limit");
-    static_assert(kColD + 384 <= kTmemCols, "TMEM column budget");
+    static_assert(kColD + 384 <= kTmemCols && kColD + 128 + 2 * kHP <= kTmemCols, "TMEM column budget");
 };
 
 // barrier / counter block at oBar (uint64 slots)
@@ -1142,7 +1142,7 @@ __device__ void forward_pass_tc(const ModelDev& M, Ctx2& c, float t_norm) {
 template <class C>
 __device__ void backward_pass_tc(const ModelDev& M, Ctx2& c) {
     constexpr int R = C::kR;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, warp_id = threadIdx.x >> 5, lane_id = threadIdx.x & 31;
     const int N = M.N, NP = M.NP, H = M.H;
     const int rows = c.rows_act;
 
@@ -1252,11 +1252,29 @@ __device__ void backward_pass_tc(const ModelDev& M, Ctx2& c) {
         }
         if (l > 0) {
             c.acc_wait();
-            tmem_foreach<C::kHP>(c.tmem, kColAcc, rows, [&](int row, int col, const float (&v)[16]) {
+            // d n_hat = (dq Wq) + (dk' Wk) + (dv' Wv): three TMEM accumulators (columns 0, kColD + 128, kColD + 128 + HP), added here
+            {
+                const int q = warp_id & 3, part = warp_id >> 2;
+                constexpr int PARTS = kCW / 4, WCOLS = C::kHP / PARTS;
+                const int row = q * 16 + lane_id;
+                if (q * 16 < rows) {
+                    const uint32_t lane_base = c.tmem + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+                    for (int cc = part * WCOLS; cc < (part + 1) * WCOLS; cc += 16) {
+                        float v0[16], v1[16], v2[16];
+                        tmem_ld16(lane_base + kColAcc + (uint32_t)cc, v0);
+                        tmem_ld16(lane_base + C::kColD + 128u + (uint32_t)cc, v1);
+                        tmem_ld16(lane_base + C::kColD + 128u + (uint32_t)C::kHP + (uint32_t)cc, v2);
+                        if (lane_id < 16 && row < rows) {
 #pragma unroll
-                for (int i = 0; i < 16; i += 4)
-                    *reinterpret_cast<float4*>(c.sNh + row * C::LDH + col + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-            });
+                            for (int i = 0; i < 16; i += 4)
+                                *reinterpret_cast<float4*>(c.sNh + row * C::LDH + cc + i) =
+                                    make_float4((v0[i] + v1[i]) + v2[i], (v0[i + 1] + v1[i + 1]) + v2[i + 1],
+                                                (v0[i + 2] + v1[i + 2]) + v2[i + 2], (v0[i + 3] + v1[i + 3]) + v2[i + 3]);
+                        }
+                    }
+                }
+            }
             tc::fence_before_sync();
             csync();
             ln_backward_rows_tc<C>(c.sN, c.sNh, H, rows, W.ln1_g, st + M.off[ST_NIN], st + M.off[ST_STAT1]);
