@@ -177,3 +177,46 @@ def test_two_rank_gather_is_rank_major(tmp_path):
                         "--master-port", "29731", str(script)], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+def test_langevin_export_and_log_option_checks(tmp_path):
+    """Host-side option validation of the Langevin mirror: same conditions and error types as the reference
+    (dynamics/langevin_cgnet.py:306-309, 352-398); nothing here touches the GPU."""
+    from dff_b200 import DffError
+    from dynamics.langevin_cgnet import Langevin
+
+    class _FF:                      # the two attributes the integrator looks for on a ForcesWrapper
+        model_gnn, training = object(), False
+
+        def force_scale(self):
+            return 1.0
+
+    x = torch.zeros(2, 4, 3)
+    kw = dict(masses=[12.0] * 4, friction=1.0, dt=1e-3, length=40, save_interval=10)
+    with pytest.raises(RuntimeError):
+        Langevin(_FF(), x, export_interval=20, **kw)                                   # filename missing
+    with pytest.raises(RuntimeError):
+        Langevin(_FF(), x, log_interval=10, log_type="write", **kw)                    # filename missing
+    with pytest.raises(ValueError):
+        Langevin(_FF(), x, export_interval=15, filename=str(tmp_path / "a"), **kw)     # not a multiple of save_interval
+    with pytest.raises(ValueError):
+        Langevin(_FF(), x, log_interval=15, log_type="print", **kw)
+    with pytest.raises(ValueError):
+        Langevin(_FF(), x, **dict(kw, length=45))                                      # save_interval must divide length
+    (tmp_path / "b_coords_000.npy").write_bytes(b"")
+    with pytest.raises(ValueError):
+        Langevin(_FF(), x, export_interval=20, filename=str(tmp_path / "b"), **kw)     # refuses to overwrite
+    (tmp_path / "c_log.txt").write_text("")
+    with pytest.raises(ValueError):
+        Langevin(_FF(), x, log_interval=10, log_type="write", filename=str(tmp_path / "c"), **kw)
+    sim = Langevin(_FF(), x, export_interval=20, filename=str(tmp_path / "d"), log_interval=20, log_type="write", **kw)
+    with pytest.raises(DffError):
+        sim.state_dict()                                                               # nothing simulated yet
+    with pytest.raises(DffError):
+        sim.simulate()                                                                 # CPU device: no fallback
+
+
+def test_pwd_pair_count_matches_triu_indices():
+    from dff_b200 import lib
+    for N, off in ((10, 3), (5, 1), (56, 3), (20, 19), (7, 7), (3, 5)):
+        assert lib().dff_pwd_num_pairs(N, off) == torch.triu_indices(N, N, offset=off).shape[1]
