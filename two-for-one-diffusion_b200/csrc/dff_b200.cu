@@ -201,7 +201,7 @@ int launch(dff_model* m, StepArgs& A, cudaStream_t stream) {
         }
         if (m->NP <= 12) return launch_tc<v2::TcCfg<12, 128>>(m, M, A, grid, stream);
         if (m->NP <= 32) return launch_tc<v2::TcCfg<32, 128>>(m, M, A, grid, stream);
-        return launch_tc<v2::TcCfg<56, 128>>(m, M, A, grid, stream);
+        return launch_tc<v2::TcCfg<56, 128, 56>>(m, M, A, grid, stream);     // one 33..56-bead sample per pass: 56-row buffers, 4-stage ring
     }
     int R, S, ctas;
     ModelDev M;

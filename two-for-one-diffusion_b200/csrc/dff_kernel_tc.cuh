@@ -30,7 +30,7 @@
 namespace dff {
 namespace v2 {
 
-constexpr int kR = 64;                    // node rows per CTA pass = MMA M
+constexpr int kMmaM = 64;                 // MMA M; a configuration uses kR <= kMmaM node rows per pass
 #ifndef DFF_TC_COMPUTE_WARPS
 #define DFF_TC_COMPUTE_WARPS 16
 #endif
@@ -39,7 +39,6 @@ constexpr int kCT = kCW * 32;                      // compute threads
 constexpr int kComputeThreads = kCT;
 constexpr int kTcThreads = kComputeThreads + 64;   // + TMA producer warp + MMA issuer warp
 constexpr int kTcStages = 3;
-constexpr int kCS = kR * 4 + 4;           // canonical chunk stride in floats (64 rows x 16 B + 16 B pad: bank spread)
 constexpr int kJobCap = 200;              // job-table entries (16 B each) cached in shared memory
 
 // TMEM column map (fp32 columns, 64 lanes used): [0, HP) block accumulator (att / ff / d m_hat / d n_hat), then at HP the
@@ -80,9 +79,10 @@ struct TcArgs {
 // HP = 64 (hidden 64) keeps the node stream in shared memory and uses 16 KB weight stages; HP = 128 (hidden 96 / 128) keeps
 // the node stream in the per-CTA global scratch (row passes only, coalesced, L2 resident) and uses 12 KB stages -- that is
 // what lets the fp32 hi/lo operands of a 64-row tile (8 bytes per element) fit 227 KB.
-template <int PN_, int HP_>
+template <int PN_, int HP_, int R_ = 64>
 struct TcCfg {
-    static constexpr int kHP = HP_, kR = v2::kR, kHC = 1, kPN = PN_;
+    static constexpr int kHP = HP_, kR = R_, kHC = 1, kPN = PN_;      // kR node rows per pass (<= 64 = the MMA M; smaller frees shared memory)
+    static constexpr int kCS = kR * 4 + 4;    // canonical chunk stride in floats (kR rows x 16 B + 16 B pad: bank spread)
     static constexpr int CWQ = 64, NCH = kHeads;
     static constexpr int LDH = kHP + 4;
     static constexpr int LDQ = 3 * CWQ + 4;
@@ -91,7 +91,7 @@ struct TcCfg {
     static constexpr int NHAT_CHUNKS = kHP / 4 + 2;          // + [x0 x1 x2 1] chunk + zero chunk (K = H + 8 for the QKV jobs)
     static constexpr int SLOT_CHUNKS = 16;
     static constexpr bool kNodeInSmem = (kHP == 64);
-    static constexpr int kStages = (PN_ > 32) ? 2 : 3;   // weight ring depth (N > 32 needs the room for p / ds)
+    static constexpr int kStages = (PN_ > 32) ? (R_ < 64 ? 4 : 2) : 3;   // weight ring depth: what the p / ds buffers leave room for
     static constexpr int kStageFloats = (kHP == 64) ? 4096 : 3072;
     static constexpr uint32_t kColD = kHP;                   // TMEM work area
     // shared memory carve-up (float offsets)
@@ -120,7 +120,7 @@ struct TcCfg {
 };
 
 // barrier / counter block at oBar (uint64 slots)
-enum { B_FULL = 0, B_EMPTY = 3, B_DQ = 6, B_ACC = 8, B_D1 = 9, B_SLOT = 10, B_COUNT = 11 };
+enum { B_FULL = 0, B_EMPTY = 4, B_DQ = 8, B_ACC = 10, B_D1 = 11, B_SLOT = 12, B_COUNT = 13 };      // room for 4 ring stages
 
 // ------------------------------------------------------------------ small PTX helpers
 __device__ __forceinline__ void csync() { asm volatile("bar.sync 1, %0;" ::"n"(kCT) : "memory"); }   // the compute warps
@@ -203,17 +203,19 @@ __device__ __forceinline__ void tmem_foreach(uint32_t tmem_base, uint32_t col, i
 }
 
 // canonical (UMMA K-major, no swizzle) operand stores with the round-to-nearest TF32 hi/lo split
+template <int CS>
 __device__ __forceinline__ void can_store4(float* hi, float* lo, int r, int k4, const float4& x) {
     float4 h, l;
     tc::split4(x, h, l);
-    *reinterpret_cast<float4*>(hi + k4 * kCS + r * 4) = h;
-    *reinterpret_cast<float4*>(lo + k4 * kCS + r * 4) = l;
+    *reinterpret_cast<float4*>(hi + k4 * CS + r * 4) = h;
+    *reinterpret_cast<float4*>(lo + k4 * CS + r * 4) = l;
 }
+template <int CS>
 __device__ __forceinline__ void can_store2(float* hi, float* lo, int r, int col, float x0, float x1) {   // col even
     float2 h, l;
     h.x = __uint_as_float((__float_as_uint(x0) + 0x1000u) & 0xffffe000u); l.x = x0 - h.x;
     h.y = __uint_as_float((__float_as_uint(x1) + 0x1000u) & 0xffffe000u); l.y = x1 - h.y;
-    const int o = (col >> 2) * kCS + r * 4 + (col & 3);
+    const int o = (col >> 2) * CS + r * 4 + (col & 3);
     *reinterpret_cast<float2*>(hi + o) = h;
     *reinterpret_cast<float2*>(lo + o) = l;
 }
@@ -309,10 +311,10 @@ __device__ __forceinline__ void row_st(float* p, const RowVec<E>& r) {
     if (E == 4) *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2 % E], r.v[3 % E]);
     else *reinterpret_cast<float2*>(p) = make_float2(r.v[0], r.v[1]);
 }
-template <int E>
+template <int E, int CS>
 __device__ __forceinline__ void row_can_store(float* hi, float* lo, int r, int col, const RowVec<E>& x) {
-    if (E == 4) can_store4(hi, lo, r, col >> 2, make_float4(x.v[0], x.v[1], x.v[2 % E], x.v[3 % E]));
-    else can_store2(hi, lo, r, col, x.v[0], x.v[1]);
+    if (E == 4) can_store4<CS>(hi, lo, r, col >> 2, make_float4(x.v[0], x.v[1], x.v[2 % E], x.v[3 % E]));
+    else can_store2<CS>(hi, lo, r, col, x.v[0], x.v[1]);
 }
 template <int E>
 __device__ __forceinline__ float row_sum(const RowVec<E>& x) {
@@ -343,7 +345,7 @@ __device__ __forceinline__ void ln_forward_rows_can(const float* sN, float* hi, 
             RowVec<E> y;
 #pragma unroll
             for (int e = 0; e < E; ++e) y.v[e] = d.v[e] * rstd * g.v[e] + b.v[e];
-            row_can_store<E>(hi, lo, r, col, y);
+            row_can_store<E, C::kCS>(hi, lo, r, col, y);
             row_st<E>(st_rows + (size_t)r * H + col, x);
         }
         if (lane == 0) { st_stats[r * 2] = mean; st_stats[r * 2 + 1] = rstd; }
@@ -391,7 +393,7 @@ __device__ __forceinline__ void gate_ln_forward_rows_can(float* sN, const float*
             RowVec<E> y;
 #pragma unroll
             for (int e = 0; e < E; ++e) y.v[e] = d.v[e] * rstd * gg.v[e] + bb.v[e];
-            row_can_store<E>(hi, lo, r, col, y);
+            row_can_store<E, C::kCS>(hi, lo, r, col, y);
         }
         if (lane == 0) { st_stats[r * 2] = mean; st_stats[r * 2 + 1] = rstd; }
     }
@@ -441,7 +443,7 @@ __device__ __forceinline__ void gate_backward_rows_can(float* sN, const float* s
             RowVec<E> da, dn;
 #pragma unroll
             for (int e = 0; e < E; ++e) { da.v[e] = d.v[e] * g + dz * wa.v[e]; dn.v[e] = d.v[e] * (1.0f - g) + dz * wb.v[e]; }
-            row_can_store<E>(hi, lo, r, col, da);
+            row_can_store<E, C::kCS>(hi, lo, r, col, da);
             row_st<E>(sN + r * C::LDH + col, dn);
         }
     }
@@ -611,10 +613,10 @@ __device__ __forceinline__ void group_weighted_rows(float (&acc)[DPL], float wre
         }
     }
 }
-template <int DPL>
+template <int DPL, int CS>
 __device__ __forceinline__ void can_store_group(float* hi, float* lo, int row, int sub, const float (&v)[DPL]) {
-    if (DPL == 4) can_store4(hi, lo, row, sub, make_float4(v[0], v[1], v[2 % DPL], v[3 % DPL]));
-    else can_store2(hi, lo, row, 2 * sub, v[0], v[1]);
+    if (DPL == 4) can_store4<CS>(hi, lo, row, sub, make_float4(v[0], v[1], v[2 % DPL], v[3 % DPL]));
+    else can_store2<CS>(hi, lo, row, 2 * sub, v[0], v[1]);
 }
 
 // Forward for head chunk hc: p_u. = softmax_j(s q_u . k'_j), o_u = sum_j p_uj v'_j - A x_u + c -> canonical slot; p -> stash.
@@ -654,7 +656,7 @@ __device__ __forceinline__ void attn_forward_rows(Ctx2& c, const LayerDev& W, in
 #pragma unroll
         for (int e2 = 0; e2 < DPL; ++e2) acc[e2] += cc[e2] - (ax[e2][0] * x0 + ax[e2][1] * x1 + ax[e2][2] * x2);
         c.slot_acquire();      // the previous out-projection has had the whole row computation to finish reading the slot
-        if (valid) can_store_group<DPL>(c.slot_hi, c.slot_lo, u, sub, acc);
+        if (valid) can_store_group<DPL, C::kCS>(c.slot_hi, c.slot_lo, u, sub, acc);
     }
 }
 
@@ -686,7 +688,7 @@ __device__ __forceinline__ void attn_backward_ds_dq(Ctx2& c, int N, int NP, bool
 #pragma unroll
             for (int e = 0; e < DPL; ++e) acc[e] *= kAttnScale;
             c.slot_acquire();
-            if (valid) can_store_group<DPL>(c.slot_hi, c.slot_lo, u, sub, acc);
+            if (valid) can_store_group<DPL, C::kCS>(c.slot_hi, c.slot_lo, u, sub, acc);
         }
     }
 }
@@ -699,7 +701,7 @@ template <class C>
 __device__ __forceinline__ void attn_backward_dkv(Ctx2& c, const LayerDev& W, int hc, int N, int NP, bool to_slot) {
     using AM = AttnMap<C>;
     constexpr int LPR = AM::LPR, DPL = AM::DPL;
-    constexpr int MR = C::kR / (kCW * AM::UPW);          // rounds a warp can have
+    constexpr int MR = (C::kR + kCW * AM::UPW - 1) / (kCW * AM::UPW);          // rounds a warp can have
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane % LPR;
     const int rows = c.rows_act;
@@ -745,7 +747,7 @@ __device__ __forceinline__ void attn_backward_dkv(Ctx2& c, const LayerDev& W, in
 #pragma unroll
         for (int rd = 0; rd < MR; ++rd) {
             const int u0 = (warp + rd * kCW) * AM::UPW + lane / LPR;
-            if (u0 < rows) can_store_group<DPL>(c.slot_hi, c.slot_lo, u0, sub, dk[rd]);
+            if (u0 < rows) can_store_group<DPL, C::kCS>(c.slot_hi, c.slot_lo, u0, sub, dk[rd]);
         }
         c.slot_post();
     }
@@ -771,7 +773,7 @@ __device__ __forceinline__ void attn_backward_dkv(Ctx2& c, const LayerDev& W, in
 #pragma unroll
         for (int rd = 0; rd < MR; ++rd) {
             const int u0 = (warp + rd * kCW) * AM::UPW + lane / LPR;
-            if (u0 < rows) can_store_group<DPL>(c.slot_hi, c.slot_lo, u0, sub, dv[rd]);
+            if (u0 < rows) can_store_group<DPL, C::kCS>(c.slot_hi, c.slot_lo, u0, sub, dv[rd]);
         }
         c.slot_post();
     } else {
@@ -888,8 +890,8 @@ __device__ __forceinline__ void attn_forward_pairs(Ctx2& c, const LayerDev& W, i
         }
         c.slot_acquire();
         if (u.valid) {
-            can_store_group<DPL>(c.slot_hi, c.slot_lo, ra, sub, oa);
-            if (u.has_b) can_store_group<DPL>(c.slot_hi, c.slot_lo, rb, sub, ob);
+            can_store_group<DPL, C::kCS>(c.slot_hi, c.slot_lo, ra, sub, oa);
+            if (u.has_b) can_store_group<DPL, C::kCS>(c.slot_hi, c.slot_lo, rb, sub, ob);
         }
     }
 }
@@ -952,8 +954,8 @@ __device__ __forceinline__ void attn_backward_ds_dq_pairs(Ctx2& c, int N, int NP
             for (int e = 0; e < DPL; ++e) { qa[e] *= kAttnScale; qb[e] *= kAttnScale; }
             c.slot_acquire();
             if (u.valid) {
-                can_store_group<DPL>(c.slot_hi, c.slot_lo, ra, sub, qa);
-                if (u.has_b) can_store_group<DPL>(c.slot_hi, c.slot_lo, rb, sub, qb);
+                can_store_group<DPL, C::kCS>(c.slot_hi, c.slot_lo, ra, sub, qa);
+                if (u.has_b) can_store_group<DPL, C::kCS>(c.slot_hi, c.slot_lo, rb, sub, qb);
             }
         }
     }
@@ -1010,8 +1012,8 @@ __device__ __forceinline__ void attn_backward_dkv_pairs(Ctx2& c, const LayerDev&
         for (int rd = 0; rd < MR; ++rd)
             if (rd * NG + gid < n_units) {
                 const PairUnit u = pair_unit<C>(rd * NG + gid, n_units, pps, N);
-                can_store_group<DPL>(c.slot_hi, c.slot_lo, u.r0 + u.ia, sub, dk[rd][0]);
-                if (u.has_b) can_store_group<DPL>(c.slot_hi, c.slot_lo, u.r0 + u.ib, sub, dk[rd][1]);
+                can_store_group<DPL, C::kCS>(c.slot_hi, c.slot_lo, u.r0 + u.ia, sub, dk[rd][0]);
+                if (u.has_b) can_store_group<DPL, C::kCS>(c.slot_hi, c.slot_lo, u.r0 + u.ib, sub, dk[rd][1]);
             }
         c.slot_post();
     }
@@ -1045,8 +1047,8 @@ __device__ __forceinline__ void attn_backward_dkv_pairs(Ctx2& c, const LayerDev&
         for (int rd = 0; rd < MR; ++rd)
             if (rd * NG + gid < n_units) {
                 const PairUnit u = pair_unit<C>(rd * NG + gid, n_units, pps, N);
-                can_store_group<DPL>(c.slot_hi, c.slot_lo, u.r0 + u.ia, sub, dv[rd][0]);
-                if (u.has_b) can_store_group<DPL>(c.slot_hi, c.slot_lo, u.r0 + u.ib, sub, dv[rd][1]);
+                can_store_group<DPL, C::kCS>(c.slot_hi, c.slot_lo, u.r0 + u.ia, sub, dv[rd][0]);
+                if (u.has_b) can_store_group<DPL, C::kCS>(c.slot_hi, c.slot_lo, u.r0 + u.ib, sub, dv[rd][1]);
             }
         c.slot_post();
     } else {
@@ -1074,7 +1076,7 @@ __device__ void forward_pass_tc(const ModelDev& M, Ctx2& c, float t_norm) {
     if (tid < R) {
         const float4 xv = (tid < rows) ? make_float4(c.sX[tid * 4], c.sX[tid * 4 + 1], c.sX[tid * 4 + 2], 1.0f)
                                        : make_float4(0.f, 0.f, 0.f, 0.f);
-        can_store4(c.nhat_hi, c.nhat_lo, tid, H / 4, xv);
+        can_store4<C::kCS>(c.nhat_hi, c.nhat_lo, tid, H / 4, xv);
     }
     csync();
     ln_forward_rows_can<C>(c.sN, c.nhat_hi, c.nhat_lo, M.layer[0].ln1_g, M.layer[0].ln1_b, H, rows, c.stash + M.off[ST_NIN],
@@ -1148,7 +1150,7 @@ __device__ void forward_pass_tc(const ModelDev& M, Ctx2& c, float t_norm) {
             if (c0 + 4 < nch64) c.post();            // TMEM work area drained: the issuer may start the next super's FF1
             c.mark(9);
             for (int ch = 0; ch < nc; ++ch) {
-                constexpr int MG = (R * 16) / kCT;       // granules (row, 4 columns) per thread
+                constexpr int MG = (R * 16 + kCT - 1) / kCT;       // granules (row, 4 columns) per thread
                 const int gc = (c0 + ch) * 64;           // hidden column of the chunk
                 float4 gq[MG];
 #pragma unroll
@@ -1167,7 +1169,7 @@ __device__ void forward_pass_tc(const ModelDev& M, Ctx2& c, float t_norm) {
 #pragma unroll
                 for (int g = 0; g < MG; ++g) {
                     const int idx = tid + g * kCT;
-                    if (idx < rows * 16) can_store4(c.slot_hi, c.slot_lo, idx >> 4, idx & 15, gq[g]);
+                    if (idx < rows * 16) can_store4<C::kCS>(c.slot_hi, c.slot_lo, idx >> 4, idx & 15, gq[g]);
                 }
                 c.slot_post();
             }
@@ -1236,7 +1238,7 @@ __device__ void backward_pass_tc(const ModelDev& M, Ctx2& c) {
             if (c0 + 4 < nch64) c.post();
             c.mark(12);
             for (int ch = 0; ch < nc; ++ch) {
-                constexpr int MG = (R * 16) / kCT;
+                constexpr int MG = (R * 16 + kCT - 1) / kCT;
                 const int gc = (c0 + ch) * 64;
                 float4 gq[MG];
 #pragma unroll
@@ -1253,7 +1255,7 @@ __device__ void backward_pass_tc(const ModelDev& M, Ctx2& c) {
 #pragma unroll
                 for (int g = 0; g < MG; ++g) {
                     const int idx = tid + g * kCT;
-                    if (idx < rows * 16) can_store4(c.slot_hi, c.slot_lo, idx >> 4, idx & 15, gq[g]);
+                    if (idx < rows * 16) can_store4<C::kCS>(c.slot_hi, c.slot_lo, idx >> 4, idx & 15, gq[g]);
                 }
                 c.slot_post();
             }
@@ -1419,8 +1421,8 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
             const uint32_t slot_hi_a = smem_u32(smem + C::oSlotHi), slot_lo_a = smem_u32(smem + C::oSlotLo);
             const uint32_t ring_a = smem_u32(smem + C::oW);
             constexpr uint64_t kDescHi = ((uint64_t)(128u >> 4) << 32) | ((uint64_t)1 << 46);      // SBO = 128 B, version 1
-            constexpr uint64_t kDescA = kDescHi | ((uint64_t)((kCS * 4) >> 4) << 16);             // LBO = chunk stride
-            constexpr uint32_t a_step = (uint32_t)(2 * kCS * 4) >> 4;                             // two 16-byte k-chunks per MMA
+            constexpr uint64_t kDescA = kDescHi | ((uint64_t)((C::kCS * 4) >> 4) << 16);             // LBO = chunk stride
+            constexpr uint32_t a_step = (uint32_t)(2 * C::kCS * 4) >> 4;                             // two 16-byte k-chunks per MMA
             for (uint32_t rep = 0; rep < reps; ++rep)
                 for (int j = 0; j < njobs; ++j) {
                     // job fields, made warp-uniform
