@@ -199,7 +199,13 @@ int launch(dff_model* m, StepArgs& A, cudaStream_t stream) {
             if (m->NP <= 32) return launch_tc<v2::TcCfg<32, 64>>(m, M, A, grid, stream);
             return launch_tc<v2::TcCfg<64, 64>>(m, M, A, grid, stream);
         }
-        if (m->NP <= 12) return launch_tc<v2::TcCfg<12, 128>>(m, M, A, grid, stream);
+        // hidden 96 / 128: passes of <= 60 rows (three 20-bead samples, twelve 5-bead samples) use 60-row buffers, which
+        // leaves room for a 4th weight stage
+        if (m->NP <= 12) {
+            if (S * N <= 60) return launch_tc<v2::TcCfg<12, 128, 60>>(m, M, A, grid, stream);
+            return launch_tc<v2::TcCfg<12, 128>>(m, M, A, grid, stream);
+        }
+        if (m->NP <= 20 && S * N <= 60) return launch_tc<v2::TcCfg<20, 128, 60>>(m, M, A, grid, stream);
         if (m->NP <= 32) return launch_tc<v2::TcCfg<32, 128>>(m, M, A, grid, stream);
         return launch_tc<v2::TcCfg<56, 128, 56>>(m, M, A, grid, stream);     // one 33..56-bead sample per pass: 56-row buffers, 4-stage ring
     }
