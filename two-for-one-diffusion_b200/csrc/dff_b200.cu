@@ -195,7 +195,10 @@ int launch(dff_model* m, StepArgs& A, cudaStream_t stream) {
         if (slices >= 4.0e9) return fail(DFF_EINVAL, "n_steps %d too large for one launch; split the call (e.g. per save interval)", A.n_steps);
         m->last_R = 64; m->last_S = S; m->last_cfg = "tc";
         if (m->HP == 64) {
-            if (m->NP <= 12) return launch_tc<v2::TcCfg<12, 64>>(m, M, A, grid, stream);
+            if (m->NP <= 12) {
+                if (S * N <= 60) return launch_tc<v2::TcCfg<12, 64, 60>>(m, M, A, grid, stream);      // 4-stage ring
+                return launch_tc<v2::TcCfg<12, 64>>(m, M, A, grid, stream);
+            }
             if (m->NP <= 32) return launch_tc<v2::TcCfg<32, 64>>(m, M, A, grid, stream);
             return launch_tc<v2::TcCfg<64, 64>>(m, M, A, grid, stream);
         }

@@ -91,9 +91,9 @@ struct TcCfg {
     static constexpr int NHAT_CHUNKS = kHP / 4 + 2;          // + [x0 x1 x2 1] chunk + zero chunk (K = H + 8 for the QKV jobs)
     static constexpr int SLOT_CHUNKS = 16;
     static constexpr bool kNodeInSmem = (kHP == 64);
-    // weight ring depth = what fits next to the row buffers: hidden 64 (16 KB stages): 3, or 2 for N > 32; hidden 96 / 128
+    // weight ring depth = what fits next to the row buffers: hidden 64 (16 KB stages): 3 (4 with 60-row buffers), 2 for N > 32; hidden 96 / 128
     // (12 KB stages): 4 when the pass has fewer than 64 rows (smaller row buffers), else 3
-    static constexpr int kStages = (HP_ == 64) ? (PN_ > 32 ? 2 : 3) : (R_ < 64 ? 4 : 3);
+    static constexpr int kStages = (HP_ == 64) ? (PN_ > 32 ? 2 : (R_ < 64 && PN_ <= 12 ? 4 : 3)) : (R_ < 64 ? 4 : 3);
     static constexpr int kStageFloats = (kHP == 64) ? 4096 : 3072;
     static constexpr uint32_t kColD = kHP;                   // TMEM work area
     // shared memory carve-up (float offsets)
