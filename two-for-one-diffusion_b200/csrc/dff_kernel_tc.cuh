@@ -1058,6 +1058,91 @@ __device__ __forceinline__ void attn_backward_dkv_pairs(Ctx2& c, const LayerDev&
     }
 }
 
+// Key-row QUADS for N > 32 (one sample per pass): a lane group owns four consecutive key rows, so the q_i / d o_i column
+// slices and the ds / p weights (one aligned float4 each) are read once per four rows; 14 quads of a 56-bead sample fit the
+// 16 lane groups in a single round (28 pairs need two).  Same outputs as attn_backward_dkv_pairs.
+template <class C>
+__device__ __forceinline__ void attn_backward_dkv_quads(Ctx2& c, const LayerDev& W, int hc, int N, int NP, bool to_slot) {
+    using AM = AttnMap<C>;
+    constexpr int LPR = AM::LPR, DPL = AM::DPL, NG = kCW * AM::UPW;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane % LPR, gid = warp * AM::UPW + lane / LPR;
+    const int qps = (N + 3) >> 2, n_units = c.S_act * qps;           // quads per sample, per pass (<= NG: checked by the caller)
+    float ax[DPL][3];
+#pragma unroll
+    for (int e = 0; e < DPL; ++e) {
+        const float4 a4 = __ldg(reinterpret_cast<const float4*>(W.A + (hc * 64 + sub * DPL + e) * 4));
+        ax[e][0] = a4.x; ax[e][1] = a4.y; ax[e][2] = a4.z;
+    }
+    const bool valid = gid < n_units;
+    const int uc = valid ? gid : n_units - 1;
+    const int s = uc / qps, r0 = s * N, j0 = (uc - s * qps) * 4;
+    const int cnt = valid ? min(4, N - j0) : 0;
+    float dk[4][DPL], dv[4][DPL];
+#pragma unroll
+    for (int h = 0; h < 4; ++h)
+#pragma unroll
+        for (int e = 0; e < DPL; ++e) { dk[h][e] = 0.f; dv[h][e] = 0.f; }
+    {
+        const float* wk = c.sDS + r0 * NP + j0;                       // j0 is a multiple of 4 and NP too: aligned float4 (pad columns are zero)
+        const float* wv = c.sP + r0 * NP + j0;
+        const float* qs = c.sQKV + r0 * C::LDQ + sub * DPL;
+        const float* os = c.sO + r0 * C::LDO + sub * DPL;
+        for (int i = 0; i < N; ++i) {
+            const float4 a = *reinterpret_cast<const float4*>(wk + i * NP), b = *reinterpret_cast<const float4*>(wv + i * NP);
+            float q[DPL], o[DPL];
+            load_cols<LPR, DPL>(q, qs + i * C::LDQ);
+            load_cols<LPR, DPL>(o, os + i * C::LDO);
+#pragma unroll
+            for (int e = 0; e < DPL; ++e) {
+                dk[0][e] = fmaf(a.x, q[e], dk[0][e]); dk[1][e] = fmaf(a.y, q[e], dk[1][e]); dk[2][e] = fmaf(a.z, q[e], dk[2][e]); dk[3][e] = fmaf(a.w, q[e], dk[3][e]);
+                dv[0][e] = fmaf(b.x, o[e], dv[0][e]); dv[1][e] = fmaf(b.y, o[e], dv[1][e]); dv[2][e] = fmaf(b.z, o[e], dv[2][e]); dv[3][e] = fmaf(b.w, o[e], dv[3][e]);
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 4; ++h)
+#pragma unroll
+            for (int e = 0; e < DPL; ++e) dk[h][e] *= kAttnScale;
+    }
+    if (to_slot) {          // job d k'
+        c.slot_acquire();
+#pragma unroll
+        for (int h = 0; h < 4; ++h)
+            if (h < cnt) can_store_group<DPL, C::kCS>(c.slot_hi, c.slot_lo, r0 + j0 + h, sub, dk[h]);
+        c.slot_post();
+    }
+    // dx_j += A_h^T (dk'_j + dv'_j - do_j): runs while the tensor core consumes d k'
+    {
+        float g[4][3];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            const int row = r0 + min(j0 + h, N - 1);
+            g[h][0] = g[h][1] = g[h][2] = 0.f;
+#pragma unroll
+            for (int e = 0; e < DPL; ++e) {
+                const float t = dk[h][e] + dv[h][e] - c.sO[row * C::LDO + sub * DPL + e];
+                g[h][0] = fmaf(ax[e][0], t, g[h][0]); g[h][1] = fmaf(ax[e][1], t, g[h][1]); g[h][2] = fmaf(ax[e][2], t, g[h][2]);
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 4; ++h) { g[h][0] = group_sum<LPR>(g[h][0]); g[h][1] = group_sum<LPR>(g[h][1]); g[h][2] = group_sum<LPR>(g[h][2]); }
+        if (sub == 0) {
+#pragma unroll
+            for (int h = 0; h < 4; ++h)
+                if (h < cnt) { const int row = r0 + j0 + h; c.sDX[row * 4] += g[h][0]; c.sDX[row * 4 + 1] += g[h][1]; c.sDX[row * 4 + 2] += g[h][2]; }
+        }
+    }
+    if (to_slot) {          // job d v'
+        c.slot_acquire();
+#pragma unroll
+        for (int h = 0; h < 4; ++h)
+            if (h < cnt) can_store_group<DPL, C::kCS>(c.slot_hi, c.slot_lo, r0 + j0 + h, sub, dv[h]);
+        c.slot_post();
+    } else {
+        csync();
+    }
+}
+
 // FF hidden block [rows][4H] TMEM -> shared (row stride LDF), so that the GELU phases can be spread over all threads
 constexpr int kLDF = 256 + 4;
 
@@ -1307,7 +1392,8 @@ __device__ void backward_pass_tc(const ModelDev& M, Ctx2& c) {
             c.mark(17);
             if (l > 0) c.slot_post(); else csync();          // every ds of the sample is in sDS before the key-row passes
             c.mark(18);
-            if (c.pairs) attn_backward_dkv_pairs<C>(c, W, hc, N, NP, l > 0);
+            if (AttnMap<C>::KPL == 2 && c.S_act * ((N + 3) >> 2) <= kCW * AttnMap<C>::UPW) attn_backward_dkv_quads<C>(c, W, hc, N, NP, l > 0);
+            else if (c.pairs) attn_backward_dkv_pairs<C>(c, W, hc, N, NP, l > 0);
             else attn_backward_dkv<C>(c, W, hc, N, NP, l > 0);
             c.mark(19);
         }
