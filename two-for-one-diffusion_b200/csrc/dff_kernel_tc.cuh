@@ -233,6 +233,7 @@ struct Ctx2 {
     uint32_t n_post, n_drain, n_acc, n_d1, n_slot;   // identical in every compute thread
     bool slot_held;
     bool pairs;            // pair-local attention routines (groups with more rows than lane groups)
+    bool quads;            // quad-local routines (N > 32: two keys per lane, one quad per warp)
     long long tw[8];       // DFF_TC_PROFILE: cycles waited on {dq, acc, d1, slot}
 #ifdef DFF_TC_PROFILE
     long long ph[32], last;
@@ -1058,6 +1059,163 @@ __device__ __forceinline__ void attn_backward_dkv_pairs(Ctx2& c, const LayerDev&
     }
 }
 
+// ------------------------------------------------------------------ query-row QUADS for N > 32 (two keys per lane)
+// A lane group (a warp) owns four consecutive query rows: the two k' (or v') rows of the lane are read once per four
+// rows (4 x 2 register tile: 96 LDS.128 for 8 dot products) and every v' / k' column slice once per four rows in the
+// P V' / dq accumulation.  14 quads of a 56-bead sample fit the 16 warps in one round.
+__device__ __forceinline__ void lane_dots8(const float* __restrict__ a, int lda, const float* __restrict__ b0, const float* __restrict__ b1,
+                                           float (&r)[4][2]) {
+    float s[4][2], t[4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { s[i][0] = s[i][1] = t[i][0] = t[i][1] = 0.f; }
+#pragma unroll 4
+    for (int k = 0; k < 16; ++k) {
+        const float4 y = *reinterpret_cast<const float4*>(b0 + 4 * k), w = *reinterpret_cast<const float4*>(b1 + 4 * k);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float4 x = *reinterpret_cast<const float4*>(a + i * lda + 4 * k);
+            s[i][0] = fmaf(x.x, y.x, s[i][0]); t[i][0] = fmaf(x.y, y.y, t[i][0]); s[i][0] = fmaf(x.z, y.z, s[i][0]); t[i][0] = fmaf(x.w, y.w, t[i][0]);
+            s[i][1] = fmaf(x.x, w.x, s[i][1]); t[i][1] = fmaf(x.y, w.y, t[i][1]); s[i][1] = fmaf(x.z, w.z, s[i][1]); t[i][1] = fmaf(x.w, w.w, t[i][1]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { r[i][0] = s[i][0] + t[i][0]; r[i][1] = s[i][1] + t[i][1]; }
+}
+
+struct QuadUnit { int r0, i0, cnt; bool valid; };
+__device__ __forceinline__ QuadUnit quad_unit(int gid, int S_act, int N) {
+    const int qps = (N + 3) >> 2, n_units = S_act * qps;
+    QuadUnit u;
+    u.valid = gid < n_units;
+    const int uc = u.valid ? gid : n_units - 1;
+    const int s = uc / qps;
+    u.r0 = s * N; u.i0 = (uc - s * qps) * 4; u.cnt = u.valid ? min(4, N - u.i0) : 0;
+    return u;
+}
+
+template <class C>
+__device__ __forceinline__ void attn_forward_quads(Ctx2& c, const LayerDev& W, int hc, int N, int NP, float* st_p) {
+    using AM = AttnMap<C>;
+    constexpr int LPR = AM::LPR, DPL = AM::DPL;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane;
+    const QuadUnit u = quad_unit(warp, c.S_act, N);
+    float cc[DPL], ax[DPL][3];
+#pragma unroll
+    for (int e = 0; e < DPL; ++e) {
+        const int col = hc * 64 + sub * DPL + e;
+        cc[e] = __ldg(W.cvec + col);
+        const float4 a4 = __ldg(reinterpret_cast<const float4*>(W.A + col * 4));
+        ax[e][0] = a4.x; ax[e][1] = a4.y; ax[e][2] = a4.z;
+    }
+    // rows of the quad (clamped for the padded tail); all four are read with one base pointer and stride LDQ
+    const int rbase = u.r0 + min(u.i0, max(N - 4, 0));               // keep the 4 rows inside the sample: shift the window back
+    const int shift = u.i0 - (rbase - u.r0);                          // rows [shift, 4) of the window are this quad's rows
+    float d[4][2];
+    lane_dots8(c.sQKV + rbase * C::LDQ, C::LDQ, c.sQKV + (u.r0 + min(sub, N - 1)) * C::LDQ + 64,
+               c.sQKV + (u.r0 + min(LPR + sub, N - 1)) * C::LDQ + 64, d);
+    const bool act0 = sub < N, act1 = LPR + sub < N;
+    float p[4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float l0 = act0 ? kAttnScale * d[i][0] : -INFINITY, l1 = act1 ? kAttnScale * d[i][1] : -INFINITY;
+        const float m = group_max<LPR>(fmaxf(l0, l1));
+        const float e0 = act0 ? expf(l0 - m) : 0.f, e1 = act1 ? expf(l1 - m) : 0.f;
+        const float ssum = group_sum<LPR>(e0 + e1);
+        p[i][0] = e0 / ssum; p[i][1] = e1 / ssum;
+        const int row = rbase + i;
+        if (u.valid && i >= shift && i - shift < u.cnt) {
+            if (sub < NP) st_p[(size_t)row * NP + sub] = p[i][0];
+            if (LPR + sub < NP) st_p[(size_t)row * NP + LPR + sub] = p[i][1];
+        }
+    }
+    float o[4][DPL];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int e = 0; e < DPL; ++e) o[i][e] = 0.f;
+#pragma unroll
+    for (int kp = 0; kp < 2; ++kp) {
+        const int kb = kp * LPR, nk = min(LPR, N - kb);
+        const float* vs = c.sQKV + (u.r0 + kb) * C::LDQ + 128 + sub * DPL;
+        for (int j = 0; j < nk; ++j) {
+            float v[DPL];
+            load_cols<LPR, DPL>(v, vs + j * C::LDQ);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float w = __shfl_sync(0xffffffffu, p[i][kp], j);
+#pragma unroll
+                for (int e = 0; e < DPL; ++e) o[i][e] = fmaf(w, v[e], o[i][e]);
+            }
+        }
+    }
+    c.slot_acquire();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int row = rbase + i;
+        const float x0 = c.sX[row * 4], x1 = c.sX[row * 4 + 1], x2 = c.sX[row * 4 + 2];
+#pragma unroll
+        for (int e = 0; e < DPL; ++e) o[i][e] += cc[e] - (ax[e][0] * x0 + ax[e][1] * x1 + ax[e][2] * x2);
+        if (u.valid && i >= shift && i - shift < u.cnt) can_store_group<DPL, C::kCS>(c.slot_hi, c.slot_lo, row, sub, o[i]);
+    }
+}
+
+template <class C>
+__device__ __forceinline__ void attn_backward_ds_dq_quads(Ctx2& c, int N, int NP, bool want_dq) {
+    using AM = AttnMap<C>;
+    constexpr int LPR = AM::LPR, DPL = AM::DPL;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane;
+    const QuadUnit u = quad_unit(warp, c.S_act, N);
+    const int rbase = u.r0 + min(u.i0, max(N - 4, 0));
+    const int shift = u.i0 - (rbase - u.r0);
+    float d[4][2];
+    lane_dots8(c.sO + rbase * C::LDO, C::LDO, c.sQKV + (u.r0 + min(sub, N - 1)) * C::LDQ + 128,
+               c.sQKV + (u.r0 + min(LPR + sub, N - 1)) * C::LDQ + 128, d);
+    const bool act0 = sub < N, act1 = LPR + sub < N;
+    float ds[4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int row = rbase + i;
+        const float p0 = act0 ? c.sP[row * NP + sub] : 0.f, p1 = act1 ? c.sP[row * NP + LPR + sub] : 0.f;
+        const float t = group_sum<LPR>(p0 * d[i][0] + p1 * d[i][1]);
+        ds[i][0] = p0 * (d[i][0] - t); ds[i][1] = p1 * (d[i][1] - t);
+        if (u.valid && i >= shift && i - shift < u.cnt) {
+            if (sub < NP) c.sDS[row * NP + sub] = ds[i][0];
+            if (LPR + sub < NP) c.sDS[row * NP + LPR + sub] = ds[i][1];
+        }
+    }
+    if (want_dq) {
+        float q[4][DPL];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int e = 0; e < DPL; ++e) q[i][e] = 0.f;
+#pragma unroll
+        for (int kp = 0; kp < 2; ++kp) {
+            const int kb = kp * LPR, nk = min(LPR, N - kb);
+            const float* ks = c.sQKV + (u.r0 + kb) * C::LDQ + 64 + sub * DPL;
+            for (int j = 0; j < nk; ++j) {
+                float v[DPL];
+                load_cols<LPR, DPL>(v, ks + j * C::LDQ);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float w = __shfl_sync(0xffffffffu, ds[i][kp], j);
+#pragma unroll
+                    for (int e = 0; e < DPL; ++e) q[i][e] = fmaf(w, v[e], q[i][e]);
+                }
+            }
+        }
+        c.slot_acquire();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+#pragma unroll
+            for (int e = 0; e < DPL; ++e) q[i][e] *= kAttnScale;
+            if (u.valid && i >= shift && i - shift < u.cnt) can_store_group<DPL, C::kCS>(c.slot_hi, c.slot_lo, rbase + i, sub, q[i]);
+        }
+    }
+}
+
 // Key-row QUADS for N > 32 (one sample per pass): a lane group owns four consecutive key rows, so the q_i / d o_i column
 // slices and the ds / p weights (one aligned float4 each) are read once per four rows; 14 quads of a 56-bead sample fit the
 // 16 lane groups in a single round (28 pairs need two).  Same outputs as attn_backward_dkv_pairs.
@@ -1195,7 +1353,12 @@ __device__ void forward_pass_tc(const ModelDev& M, Ctx2& c, float t_norm) {
                 c.mark(2);
             }
             // logits, softmax, P V' - A x_i + c -> canonical operand of the out-projection (row-local, no barrier inside)
-            if (c.pairs) attn_forward_pairs<C>(c, W, hc, N, NP, st + M.off[ST_P] + (size_t)hc * R * NP);
+            bool done_q = false;
+            if constexpr (AttnMap<C>::KPL == 2) {
+                if (c.quads) { attn_forward_quads<C>(c, W, hc, N, NP, st + M.off[ST_P] + (size_t)hc * R * NP); done_q = true; }
+            }
+            if (done_q) { }
+            else if (c.pairs) attn_forward_pairs<C>(c, W, hc, N, NP, st + M.off[ST_P] + (size_t)hc * R * NP);
             else attn_forward_rows<C>(c, W, hc, N, NP, st + M.off[ST_P] + (size_t)hc * R * NP);
             c.mark(3);
             c.slot_post();
@@ -1387,12 +1550,17 @@ __device__ void backward_pass_tc(const ModelDev& M, Ctx2& c) {
                 c.dq_release();
                 c.mark(16);
             }
-            if (c.pairs) attn_backward_ds_dq_pairs<C>(c, N, NP, l > 0);
+            bool done_q = false;
+            if constexpr (AttnMap<C>::KPL == 2) {
+                if (c.quads) { attn_backward_ds_dq_quads<C>(c, N, NP, l > 0); done_q = true; }
+            }
+            if (done_q) { }
+            else if (c.pairs) attn_backward_ds_dq_pairs<C>(c, N, NP, l > 0);
             else attn_backward_ds_dq<C>(c, N, NP, l > 0);
             c.mark(17);
             if (l > 0) c.slot_post(); else csync();          // every ds of the sample is in sDS before the key-row passes
             c.mark(18);
-            if (AttnMap<C>::KPL == 2 && c.S_act * ((N + 3) >> 2) <= kCW * AttnMap<C>::UPW) attn_backward_dkv_quads<C>(c, W, hc, N, NP, l > 0);
+            if (c.quads) attn_backward_dkv_quads<C>(c, W, hc, N, NP, l > 0);
             else if (c.pairs) attn_backward_dkv_pairs<C>(c, W, hc, N, NP, l > 0);
             else attn_backward_dkv<C>(c, W, hc, N, NP, l > 0);
             c.mark(19);
@@ -1604,6 +1772,7 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
             c.S_act = my_n / my_groups + (g < my_n % my_groups ? 1 : 0);
             s_next += c.S_act;
             c.rows_act = c.S_act * N;
+            c.quads = AttnMap<C>::KPL == 2 && N >= 4 && c.S_act * ((N + 3) >> 2) <= kCW;
 #ifdef DFF_TC_PAIRS_ALWAYS
             c.pairs = true;
 #else
