@@ -1059,10 +1059,11 @@ __device__ __forceinline__ void attn_backward_dkv_pairs(Ctx2& c, const LayerDev&
     }
 }
 
-// ------------------------------------------------------------------ query-row QUADS for N > 32 (two keys per lane)
+// ------------------------------------------------------------------ query-row QUADS for full-warp lane groups (N > 12)
 // A lane group (a warp) owns four consecutive query rows: the two k' (or v') rows of the lane are read once per four
 // rows (4 x 2 register tile: 96 LDS.128 for 8 dot products) and every v' / k' column slice once per four rows in the
 // P V' / dq accumulation.  14 quads of a 56-bead sample fit the 16 warps in one round.
+template <int KPL>
 __device__ __forceinline__ void lane_dots8(const float* __restrict__ a, int lda, const float* __restrict__ b0, const float* __restrict__ b1,
                                            float (&r)[4][2]) {
     float s[4][2], t[4][2];
@@ -1070,12 +1071,13 @@ __device__ __forceinline__ void lane_dots8(const float* __restrict__ a, int lda,
     for (int i = 0; i < 4; ++i) { s[i][0] = s[i][1] = t[i][0] = t[i][1] = 0.f; }
 #pragma unroll 4
     for (int k = 0; k < 16; ++k) {
-        const float4 y = *reinterpret_cast<const float4*>(b0 + 4 * k), w = *reinterpret_cast<const float4*>(b1 + 4 * k);
+        const float4 y = *reinterpret_cast<const float4*>(b0 + 4 * k);
+        const float4 w = (KPL == 2) ? *reinterpret_cast<const float4*>(b1 + 4 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const float4 x = *reinterpret_cast<const float4*>(a + i * lda + 4 * k);
             s[i][0] = fmaf(x.x, y.x, s[i][0]); t[i][0] = fmaf(x.y, y.y, t[i][0]); s[i][0] = fmaf(x.z, y.z, s[i][0]); t[i][0] = fmaf(x.w, y.w, t[i][0]);
-            s[i][1] = fmaf(x.x, w.x, s[i][1]); t[i][1] = fmaf(x.y, w.y, t[i][1]); s[i][1] = fmaf(x.z, w.z, s[i][1]); t[i][1] = fmaf(x.w, w.w, t[i][1]);
+            if (KPL == 2) { s[i][1] = fmaf(x.x, w.x, s[i][1]); t[i][1] = fmaf(x.y, w.y, t[i][1]); s[i][1] = fmaf(x.z, w.z, s[i][1]); t[i][1] = fmaf(x.w, w.w, t[i][1]); }
         }
     }
 #pragma unroll
@@ -1112,7 +1114,7 @@ __device__ __forceinline__ void attn_forward_quads(Ctx2& c, const LayerDev& W, i
     const int rbase = u.r0 + min(u.i0, max(N - 4, 0));               // keep the 4 rows inside the sample: shift the window back
     const int shift = u.i0 - (rbase - u.r0);                          // rows [shift, 4) of the window are this quad's rows
     float d[4][2];
-    lane_dots8(c.sQKV + rbase * C::LDQ, C::LDQ, c.sQKV + (u.r0 + min(sub, N - 1)) * C::LDQ + 64,
+    lane_dots8<AM::KPL>(c.sQKV + rbase * C::LDQ, C::LDQ, c.sQKV + (u.r0 + min(sub, N - 1)) * C::LDQ + 64,
                c.sQKV + (u.r0 + min(LPR + sub, N - 1)) * C::LDQ + 64, d);
     const bool act0 = sub < N, act1 = LPR + sub < N;
     float p[4][2];
@@ -1135,7 +1137,7 @@ __device__ __forceinline__ void attn_forward_quads(Ctx2& c, const LayerDev& W, i
 #pragma unroll
         for (int e = 0; e < DPL; ++e) o[i][e] = 0.f;
 #pragma unroll
-    for (int kp = 0; kp < 2; ++kp) {
+    for (int kp = 0; kp < AM::KPL; ++kp) {
         const int kb = kp * LPR, nk = min(LPR, N - kb);
         const float* vs = c.sQKV + (u.r0 + kb) * C::LDQ + 128 + sub * DPL;
         for (int j = 0; j < nk; ++j) {
@@ -1170,7 +1172,7 @@ __device__ __forceinline__ void attn_backward_ds_dq_quads(Ctx2& c, int N, int NP
     const int rbase = u.r0 + min(u.i0, max(N - 4, 0));
     const int shift = u.i0 - (rbase - u.r0);
     float d[4][2];
-    lane_dots8(c.sO + rbase * C::LDO, C::LDO, c.sQKV + (u.r0 + min(sub, N - 1)) * C::LDQ + 128,
+    lane_dots8<AM::KPL>(c.sO + rbase * C::LDO, C::LDO, c.sQKV + (u.r0 + min(sub, N - 1)) * C::LDQ + 128,
                c.sQKV + (u.r0 + min(LPR + sub, N - 1)) * C::LDQ + 128, d);
     const bool act0 = sub < N, act1 = LPR + sub < N;
     float ds[4][2];
@@ -1192,7 +1194,7 @@ __device__ __forceinline__ void attn_backward_ds_dq_quads(Ctx2& c, int N, int NP
 #pragma unroll
             for (int e = 0; e < DPL; ++e) q[i][e] = 0.f;
 #pragma unroll
-        for (int kp = 0; kp < 2; ++kp) {
+        for (int kp = 0; kp < AM::KPL; ++kp) {
             const int kb = kp * LPR, nk = min(LPR, N - kb);
             const float* ks = c.sQKV + (u.r0 + kb) * C::LDQ + 64 + sub * DPL;
             for (int j = 0; j < nk; ++j) {
@@ -1354,7 +1356,7 @@ __device__ void forward_pass_tc(const ModelDev& M, Ctx2& c, float t_norm) {
             }
             // logits, softmax, P V' - A x_i + c -> canonical operand of the out-projection (row-local, no barrier inside)
             bool done_q = false;
-            if constexpr (AttnMap<C>::KPL == 2) {
+            if constexpr (AttnMap<C>::LPR == 32) {
                 if (c.quads) { attn_forward_quads<C>(c, W, hc, N, NP, st + M.off[ST_P] + (size_t)hc * R * NP); done_q = true; }
             }
             if (done_q) { }
@@ -1551,7 +1553,7 @@ __device__ void backward_pass_tc(const ModelDev& M, Ctx2& c) {
                 c.mark(16);
             }
             bool done_q = false;
-            if constexpr (AttnMap<C>::KPL == 2) {
+            if constexpr (AttnMap<C>::LPR == 32) {
                 if (c.quads) { attn_backward_ds_dq_quads<C>(c, N, NP, l > 0); done_q = true; }
             }
             if (done_q) { }
@@ -1772,7 +1774,7 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
             c.S_act = my_n / my_groups + (g < my_n % my_groups ? 1 : 0);
             s_next += c.S_act;
             c.rows_act = c.S_act * N;
-            c.quads = AttnMap<C>::KPL == 2 && N >= 4 && c.S_act * ((N + 3) >> 2) <= kCW;
+            c.quads = AttnMap<C>::LPR == 32 && c.rows_act > kCW && N >= 4 && c.S_act * ((N + 3) >> 2) <= kCW;   // full-warp groups, more rows than warps
 #ifdef DFF_TC_PAIRS_ALWAYS
             c.pairs = true;
 #else
