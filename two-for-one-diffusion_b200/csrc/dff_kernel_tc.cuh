@@ -1100,8 +1100,8 @@ __device__ __forceinline__ void attn_forward_quads(Ctx2& c, const LayerDev& W, i
     using AM = AttnMap<C>;
     constexpr int LPR = AM::LPR, DPL = AM::DPL;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int sub = lane;
-    const QuadUnit u = quad_unit(warp, c.S_act, N);
+    const int sub = lane % LPR, gbase = lane - sub;
+    const QuadUnit u = quad_unit(warp * AM::UPW + lane / LPR, c.S_act, N);
     float cc[DPL], ax[DPL][3];
 #pragma unroll
     for (int e = 0; e < DPL; ++e) {
@@ -1145,7 +1145,7 @@ __device__ __forceinline__ void attn_forward_quads(Ctx2& c, const LayerDev& W, i
             load_cols<LPR, DPL>(v, vs + j * C::LDQ);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const float w = __shfl_sync(0xffffffffu, p[i][kp], j);
+                const float w = __shfl_sync(0xffffffffu, p[i][kp], gbase + j);
 #pragma unroll
                 for (int e = 0; e < DPL; ++e) o[i][e] = fmaf(w, v[e], o[i][e]);
             }
@@ -1167,8 +1167,8 @@ __device__ __forceinline__ void attn_backward_ds_dq_quads(Ctx2& c, int N, int NP
     using AM = AttnMap<C>;
     constexpr int LPR = AM::LPR, DPL = AM::DPL;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int sub = lane;
-    const QuadUnit u = quad_unit(warp, c.S_act, N);
+    const int sub = lane % LPR, gbase = lane - sub;
+    const QuadUnit u = quad_unit(warp * AM::UPW + lane / LPR, c.S_act, N);
     const int rbase = u.r0 + min(u.i0, max(N - 4, 0));
     const int shift = u.i0 - (rbase - u.r0);
     float d[4][2];
@@ -1202,7 +1202,7 @@ __device__ __forceinline__ void attn_backward_ds_dq_quads(Ctx2& c, int N, int NP
                 load_cols<LPR, DPL>(v, ks + j * C::LDQ);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const float w = __shfl_sync(0xffffffffu, ds[i][kp], j);
+                    const float w = __shfl_sync(0xffffffffu, ds[i][kp], gbase + j);
 #pragma unroll
                     for (int e = 0; e < DPL; ++e) q[i][e] = fmaf(w, v[e], q[i][e]);
                 }
@@ -1356,7 +1356,7 @@ __device__ void forward_pass_tc(const ModelDev& M, Ctx2& c, float t_norm) {
             }
             // logits, softmax, P V' - A x_i + c -> canonical operand of the out-projection (row-local, no barrier inside)
             bool done_q = false;
-            if constexpr (AttnMap<C>::LPR == 32) {
+            {
                 if (c.quads) { attn_forward_quads<C>(c, W, hc, N, NP, st + M.off[ST_P] + (size_t)hc * R * NP); done_q = true; }
             }
             if (done_q) { }
@@ -1553,7 +1553,7 @@ __device__ void backward_pass_tc(const ModelDev& M, Ctx2& c) {
                 c.mark(16);
             }
             bool done_q = false;
-            if constexpr (AttnMap<C>::LPR == 32) {
+            {
                 if (c.quads) { attn_backward_ds_dq_quads<C>(c, N, NP, l > 0); done_q = true; }
             }
             if (done_q) { }
@@ -1774,7 +1774,11 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
             c.S_act = my_n / my_groups + (g < my_n % my_groups ? 1 : 0);
             s_next += c.S_act;
             c.rows_act = c.S_act * N;
-            c.quads = AttnMap<C>::LPR == 32 && c.rows_act > kCW && N >= 4 && c.S_act * ((N + 3) >> 2) <= kCW;   // full-warp groups, more rows than warps
+#ifndef DFF_TC_QUADS16
+#define DFF_TC_QUADS16 0
+#endif
+            c.quads = (AttnMap<C>::LPR == 32 || DFF_TC_QUADS16) && c.rows_act > kCW * AttnMap<C>::UPW && N >= 4 &&
+                      c.S_act * ((N + 3) >> 2) <= kCW * AttnMap<C>::UPW;      // more rows than lane groups, one quad per group
 #ifdef DFF_TC_PAIRS_ALWAYS
             c.pairs = true;
 #else
