@@ -209,3 +209,20 @@ def test_tcgen05_and_mma_sync_agree_hidden_96_128(mol, monkeypatch):
         assert rel_err(eps, f64) < FORCE_RTOL and rel_err(en, e64) < FORCE_RTOL, (cfg, rel_err(eps, f64))
         out[cfg] = eps.cpu()
     assert rel_err(out["tc"], out["legacy"]) < FORCE_RTOL
+
+
+@pytest.mark.parametrize("N,H,B", [(13, 64, 9), (17, 128, 5), (23, 96, 4), (31, 64, 3), (33, 128, 3), (41, 64, 2), (50, 128, 2), (4, 64, 40), (3, 128, 11)])
+def test_tcgen05_odd_bead_counts_vs_oracle(N, H, B, monkeypatch):
+    """Bead counts that do not divide the 2- and 4-row attention tiles, both lane-group widths and both key-per-lane
+    settings (row-, pair- and quad-local routines with partial tails), against the fp64 oracle."""
+    from oracle import collapsed_ref, score_ref
+    from oracle.weights import synthetic_net_params
+    monkeypatch.delenv("DFF_CONFIG", raising=False)
+    p = synthetic_net_params(N, H, 2, seed=N)
+    eng = _engine(p, max_batch=64)
+    x = torch.randn(B, N, 3, generator=torch.Generator().manual_seed(N + H)) * 0.9
+    x = x - x.mean(1, keepdim=True)
+    f64, e64, _ = collapsed_ref.forward_backward(score_ref.to_dtype(p, torch.float64), x.double(), 0.3)
+    eps, en = eng.score(x.cuda(), 0.3, want_energy=True)
+    assert eng.last_config == "tc"
+    assert rel_err(eps, f64) < FORCE_RTOL and rel_err(en, e64) < FORCE_RTOL, (N, H, rel_err(eps, f64), rel_err(en, e64))
