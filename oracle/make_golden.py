@@ -37,6 +37,12 @@ MOLS = {
     "ala2_fold1": ("alanine/fold1", "ala2_cg.pdb", 0.9449278712272644, 300, 12.8),
     "trp_cage": ("trp_cage", "2JOF-0-c-alpha.pdb", 5.08211088180542, 290, 12.0),
     "protein_g": ("protein_g", "NuG2-0-c-alpha.pdb", 6.354289531707764, 350, 12.0),
+    # the other five shipped checkpoints (SURVEY 4 tier 1: all nine)
+    "bba": ("bba", "1FME-0-c-alpha.pdb", 6.294918537139893, 325, 12.0),
+    "villin": ("villin", "2F4K-0-c-alpha.pdb", 6.082900047302246, 360, 12.0),
+    "ala2_fold2": ("alanine/fold2", "ala2_cg.pdb", 0.944965124130249, 300, 12.8),
+    "ala2_fold3": ("alanine/fold3", "ala2_cg.pdb", 0.9452606439590454, 300, 12.8),
+    "ala2_fold4": ("alanine/fold4", "ala2_cg.pdb", 0.9454087018966675, 300, 12.8),
 }
 
 
@@ -165,11 +171,15 @@ def synth_fixture(get_model, shapes):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--skip-full", action="store_true")
+    ap.add_argument("--only", default="", help="comma-separated molecule names (default: all); implies no synthetic fixture")
     a = ap.parse_args()
+    only = [m for m in a.only.split(",") if m]
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     get_model, GaussianDiffusion, LangevinDiffusion = import_reference()
     for name, (ckdir, pdb, std, temp, mass) in MOLS.items():
+        if only and name not in only:
+            continue
         ddpm, ema, n = build_ddpm(get_model, GaussianDiffusion, ckdir, std)
         torch.save({k: v.clone() for k, v in ema.items()}, os.path.join(OUT, f"weights_{name}.pt"))
         meta = dict(mol=name, num_beads=n, std=std, temp=temp, mass=mass)
@@ -183,6 +193,9 @@ def main():
             full = ddpm.sample(batch_size=2)
             torch.save(dict(meta=meta, rng_state=state, seed=4242, sample=full),
                        os.path.join(OUT, "ddpm_full_ala2.pt"))
+    if only:
+        print("done (subset)")
+        return
     shapes = [(10, 64, 3, 1, 5), (20, 128, 3, 2, 3), (28, 96, 3, 3, 3), (35, 128, 3, 4, 2), (56, 128, 3, 5, 2),
               (5, 96, 2, 6, 7), (7, 64, 1, 7, 3), (64, 128, 2, 8, 2)]
     torch.save(synth_fixture(get_model, shapes), os.path.join(OUT, "score_synth.pt"))

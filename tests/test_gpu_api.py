@@ -161,6 +161,69 @@ def test_distribution_matches_reference_samples():
             assert sampler_ref.js_divergence(h.numpy(), r["hist"].numpy()) < 5e-3, (mol, rng)
 
 
+@pytest.mark.parametrize("rng", ["torch", "philox"])
+def test_langevin_distribution_matches_reference_run(rng):
+    """Distributional parity of MD trajectories (north_star): the reference's own 64 x 2000-step BAOAB run on ala2 (t* = 8,
+    frames every 20 steps; tests/golden/dist_reference.pt["ala2_fold1"]["langevin"]) against the same protocol on the GPU
+    with 512 simulations started from GPU iid samples.  Frames of one trajectory are correlated, so the standard error of a
+    per-pair mean uses the number of independent simulations, not the number of frames."""
+    from dynamics.langevin import LangevinDiffusion
+    from oracle import sampler_ref
+    r = torch.load(os.path.join(GOLDEN, "dist_reference.pt"))["ala2_fold1"]["langevin"]
+    ddpm = _ddpm("ala2_fold1", rng=rng)
+    torch.manual_seed(17)
+    init = ddpm.sample(batch_size=512)
+    sim = LangevinDiffusion(ddpm, init, r["steps"], save_interval=r["save_interval"], t=r["t"], diffusion_steps=1000, temp_data=300,
+                            temp_sim=300, dt=None, masses=[12.8] * 5, friction=1.0, kb="consistent", rng=rng)
+    traj = sim.sample().cpu()
+    assert traj.shape == (512 * (r["steps"] // r["save_interval"]), 5, 3) and torch.isfinite(traj).all()
+    d = sampler_ref.pwd_triu(traj)
+    se = (r["std"] ** 2 / r["n_sims"] + d.std(0) ** 2 / 512).sqrt()
+    zscore = ((d.mean(0) - r["mean"]).abs() / se).max()
+    assert float(zscore) < 5.0, (rng, float(zscore))
+    assert float(((d.std(0) / r["std"]) - 1).abs().max()) < 0.25, rng
+    h = torch.histc(d.flatten(), bins=60, min=0.0, max=r["hi"])
+    assert sampler_ref.js_divergence(h.numpy(), r["hist"].numpy()) < 5e-3, rng
+
+
+def test_forward_refuses_non_uniform_t_and_foreign_h():
+    """the kernel evaluates one noise level per call; a per-sample t or a non-identity h must raise, not silently
+    take t[0] / ignore h (reference: graph_transformer.py:91, 99-103)."""
+    from dff_b200 import DffError
+    ddpm = _ddpm("chignolin")
+    x = load("score_chignolin.pt")["cases"][0]["x"].cuda()
+    B = x.shape[0]
+    ok = ddpm.model(x, ddpm.h, torch.full((B, 1, 1), 0.02, device="cuda"))
+    assert ok.shape == x.shape
+    t_bad = torch.full((B,), 0.02, device="cuda"); t_bad[-1] = 0.5
+    with pytest.raises(DffError, match="same t"):
+        ddpm.model(x, ddpm.h, t_bad)
+    with pytest.raises(DffError, match="entries"):
+        ddpm.model(x, ddpm.h, torch.full((B + 1,), 0.02, device="cuda"))
+    with pytest.raises(DffError, match="identity"):
+        ddpm.model(x, torch.ones(10, 10), torch.full((B,), 0.02, device="cuda"))
+    with pytest.raises(DffError):
+        ddpm.model(x, torch.eye(9), torch.full((B,), 0.02, device="cuda"))
+
+
+def test_simulate_beyond_length_returns_only_real_frames():
+    """simulate(sub_interval) past the end of the run must not hand back uninitialised frames nor consume RNG draws."""
+    ddpm = _ddpm("chignolin")
+    init = load("langevin_chignolin.pt")["runs"][0]["init_mol"] / load("score_chignolin.pt")["meta"]["std"]
+    a = _langevin(ddpm, init, 40, 10, "torch", 5)
+    first = a.simulate(sub_interval=30)
+    state = a.rng.get_state().clone()
+    tail = a.simulate(sub_interval=30)                 # only 10 steps are left
+    assert first.shape[1] == 3 and tail.shape[1] == 1 and a.t == 40
+    b = _langevin(ddpm, init, 40, 10, "torch", 5)
+    full = b.simulate()
+    import numpy as np
+    assert np.array_equal(np.concatenate([first, tail], 1), full)
+    s2 = a.rng.get_state().clone()
+    empty = a.simulate(sub_interval=10)                # nothing left: no frames, RNG untouched
+    assert empty.shape[1] == 0 and torch.equal(a.rng.get_state(), s2) and not torch.equal(state, s2)
+
+
 def _langevin(ddpm, init, length, si, rng, seed, friction=1.0, **kw):
     """A bare dynamics.langevin_cgnet.Langevin on the chignolin force field (the object LangevinDiffusion builds)."""
     from dynamics.langevin import ForcesWrapper

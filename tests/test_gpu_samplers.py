@@ -5,7 +5,7 @@ import math
 import pytest
 import torch
 
-from helpers import MOLS, load, net_params, rel_err, schedule
+from helpers import ALL_MOLS, MOLS, load, net_params, rel_err, schedule
 
 pytestmark = pytest.mark.gpu
 
@@ -23,7 +23,7 @@ def _sched_dev(mol):
     return [s[k].cuda().contiguous() for k in SCHED_KEYS]
 
 
-@pytest.mark.parametrize("mol", MOLS)
+@pytest.mark.parametrize("mol", ALL_MOLS)
 def test_ddpm_chain_slices(mol):
     eng = _engine(net_params(mol))
     sched = _sched_dev(mol)
@@ -57,7 +57,7 @@ def _md_params(sched, std, r):
     return p
 
 
-@pytest.mark.parametrize("mol", MOLS)
+@pytest.mark.parametrize("mol", ALL_MOLS)
 def test_langevin_runs(mol):
     g = load(f"langevin_{mol}.pt")
     std = g["meta"]["std"]
@@ -176,3 +176,59 @@ def test_host_buffer_entry_points_match_device_path():
     eng.langevin_steps(xd, vd, 12, prm, mass.cuda(), noise=None, seed=77, offset=0, save_interval=4, frames=fd, ke=kd)
     assert torch.equal(xh, xd.cpu()) and torch.equal(vh, vd.cpu()) and torch.equal(fh, fd.cpu()) and torch.equal(kh, kd.cpu())
     assert torch.isfinite(fh).all()
+
+
+# ---- long trajectories: one launch integrates a whole save interval (250 MD steps) / a long slice of the reverse chain
+# tests/golden/long_<mol>.pt holds the unmodified reference's run on injected noise and the same run integrated in fp64 by
+# the oracle: the reference's own fp32 drift from fp64 is 2e-7 .. 4e-7 at every saved frame up to step 250 (the dynamics are
+# strongly damped at dt ~ 1e-3 ps, errors do not amplify), so the per-step-count tolerances below are the per-step force
+# tolerance (1e-4 on forces -> <= 2e-4 on positions) and do NOT need to grow with the number of steps.
+LONG_TOL = {50: 2e-4, 100: 2e-4, 250: 2e-4}
+
+
+@pytest.mark.parametrize("mol", ["chignolin", "ala2_fold1", "trp_cage"])
+def test_long_langevin_single_launch_vs_reference(mol):
+    g = load(f"long_{mol}.pt")
+    std = g["meta"]["std"]
+    eng = _engine(net_params(mol))
+    sched = schedule(mol)
+    for r in g["runs"]:
+        prm = _md_params(sched, std, r)
+        B, N = r["init_mol"].shape[:2]
+        x = (r["init_mol"] / std).cuda().contiguous()
+        v = torch.zeros_like(x) if r["friction"] is not None else None
+        nf = r["steps"] // r["save_interval"]
+        frames = torch.zeros(nf, B, N, 3, device="cuda")
+        ke = torch.zeros(nf, B, device="cuda")
+        mass = torch.tensor(r["masses"], dtype=torch.float32, device="cuda")
+        l0 = eng.launches
+        eng.langevin_steps(x, v, r["steps"], prm, mass, noise=r["noise"].cuda().contiguous(), save_interval=r["save_interval"],
+                           frames=frames, ke=ke)
+        assert eng.launches == l0 + 1                                        # the whole run is ONE launch
+        got = frames.permute(1, 0, 2, 3).cpu() * std                         # [B, nf, N, 3]
+        ref = r["traj"].reshape(B, nf, N, 3)
+        ref64 = r["traj64"].reshape(B, nf, N, 3)
+        for f in range(nf):
+            n_steps = (f + 1) * r["save_interval"]
+            tol = LONG_TOL[max(k for k in LONG_TOL if k <= max(n_steps, 50))]
+            e_ref, e_64 = rel_err(got[:, f], ref[:, f]), rel_err(got[:, f], ref64[:, f])
+            assert e_ref < tol and e_64 < tol, (mol, r["friction"], n_steps, e_ref, e_64)
+        if r["kinetic"] is not None:
+            assert rel_err(ke.t(), r["kinetic"]) < 5e-4, (mol, rel_err(ke.t(), r["kinetic"]))
+        assert eng.read_flags() & 4 == 0
+
+
+@pytest.mark.parametrize("mol", ["chignolin", "ala2_fold1", "trp_cage"])
+def test_long_ddpm_slice_single_launch_vs_reference(mol):
+    ch = load(f"long_{mol}.pt")["chain"]
+    eng = _engine(net_params(mol))
+    sched = _sched_dev(mol)
+    x = ch["x_init"].cuda().contiguous()
+    noise = ch["noise"].cuda().contiguous()
+    for k in range(3):                                                        # 3 launches of 20 steps, checked after each
+        eng.ddpm_steps(x, ch["t_start"] - 20 * k, 20, 1000, sched, noise=noise[20 * k:20 * k + 20].contiguous())
+        assert rel_err(x, ch["x_every20"][k]) < STEP_RTOL, (mol, k, rel_err(x, ch["x_every20"][k]))
+    x1 = ch["x_init"].cuda().contiguous()
+    eng.ddpm_steps(x1, ch["t_start"], 60, 1000, sched, noise=noise)           # and all 60 in ONE launch
+    assert torch.equal(x1, x)
+    assert rel_err(x1, ch["x64_last"]) < STEP_RTOL

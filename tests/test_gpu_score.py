@@ -2,7 +2,7 @@
 import pytest
 import torch
 
-from helpers import FORCE_RTOL, MOLS, load, net_params, rel_err
+from helpers import ALL_MOLS, FORCE_RTOL, MOLS, load, net_params, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -12,7 +12,7 @@ def _engine(params, max_batch=64):
     return ScoreEngine(params, device="cuda:0", max_batch=max_batch)
 
 
-@pytest.mark.parametrize("mol", MOLS)
+@pytest.mark.parametrize("mol", ALL_MOLS)
 def test_forces_and_energy_vs_reference_golden(mol):
     eng = _engine(net_params(mol))
     for c in load(f"score_{mol}.pt")["cases"]:
@@ -226,3 +226,57 @@ def test_tcgen05_odd_bead_counts_vs_oracle(N, H, B, monkeypatch):
     eps, en = eng.score(x.cuda(), 0.3, want_energy=True)
     assert eng.last_config == "tc"
     assert rel_err(eps, f64) < FORCE_RTOL and rel_err(en, e64) < FORCE_RTOL, (N, H, rel_err(eps, f64), rel_err(en, e64))
+
+
+def test_worst_case_force_error_all_nine_checkpoints(capsys):
+    """Accuracy headroom, printed: worst max-norm and worst per-sample relative force error over the 5 noise levels of all
+    nine shipped checkpoints, against the reference's fp32 outputs and against the fp64 oracle.  Gate: 1e-4 (north_star);
+    the printed numbers are what DESIGN.md quotes."""
+    from oracle import collapsed_ref, score_ref
+    worst = {}
+    for mol in ALL_MOLS:
+        p = net_params(mol)
+        p64 = score_ref.to_dtype(p, torch.float64)
+        eng = _engine(p)
+        w_ref = w_64 = w_samp = 0.0
+        for c in load(f"score_{mol}.pt")["cases"]:
+            eps, _ = eng.score(c["x"].cuda().contiguous(), c["t_norm"])
+            f64, _, _ = collapsed_ref.forward_backward(p64, c["x"].double(), c["t_norm"])
+            w_ref = max(w_ref, rel_err(eps, c["forces"]))
+            w_64 = max(w_64, rel_err(eps, f64))
+            per = (eps.cpu().double() - f64).flatten(1).abs().amax(1) / f64.flatten(1).abs().amax(1)     # per-sample max-norm
+            w_samp = max(w_samp, float(per.max()))
+        worst[mol] = (w_ref, w_64, w_samp)
+    with capsys.disabled():
+        print()
+        for mol, (a, b, c_) in worst.items():
+            print(f"[force error] {mol:11s} vs reference fp32 {a:.2e}   vs fp64 oracle {b:.2e}   worst single sample vs fp64 {c_:.2e}")
+    assert max(v[0] for v in worst.values()) < FORCE_RTOL and max(v[1] for v in worst.values()) < FORCE_RTOL
+    assert max(v[2] for v in worst.values()) < 2 * FORCE_RTOL
+
+
+@pytest.mark.parametrize("mol,batch", [("trp_cage", 1024), ("protein_g", 512), ("chignolin", 4096), ("villin", 300), ("bba", 333)])
+def test_bench_batch_sizes_vs_oracle(mol, batch):
+    """The BASELINE batch sizes (C3 / C4 / C5): every CTA walks several row groups and, for hidden 96 / 128, re-uses its global
+    node-stream scratch between them.  A strided subset of samples that covers the first / last group of the first, a middle
+    and the last CTA is compared with the fp64 oracle; the whole batch must be finite and translation-consistent."""
+    from oracle import collapsed_ref, score_ref
+    p = net_params(mol)
+    N = p["node_embedding.weight"].shape[1] - 1
+    eng = _engine(p, max_batch=batch)
+    base = load(f"score_{mol}.pt")["cases"][0]["x"]
+    g = torch.Generator().manual_seed(batch)
+    x = base[torch.arange(batch) % base.shape[0]] + 0.05 * torch.randn(batch, N, 3, generator=g)
+    x = (x - x.mean(1, keepdim=True)).contiguous()
+    eps, en = eng.score(x.cuda(), 0.02, want_energy=True)
+    assert eng.last_config == "tc" and torch.isfinite(eps).all() and torch.isfinite(en).all()
+    per_cta = -(-batch // 148)
+    idx = sorted(set([0, 1, per_cta - 1, per_cta, per_cta + 1, 2 * per_cta - 1, batch // 2, batch // 2 + 1, batch - per_cta - 1,
+                      batch - per_cta, batch - 2, batch - 1] + list(range(3, batch, max(batch // 12, 1)))))
+    idx = [i for i in idx if 0 <= i < batch]
+    f64, e64, _ = collapsed_ref.forward_backward(score_ref.to_dtype(p, torch.float64), x[idx].double(), 0.02)
+    assert rel_err(eps[idx], f64) < FORCE_RTOL, (mol, rel_err(eps[idx], f64))
+    assert rel_err(en[idx], e64) < FORCE_RTOL, (mol, rel_err(en[idx], e64))
+    # the same samples placed in different CTAs / row groups (other group sizes, other attention routines) agree to rounding
+    eps2, _ = eng.score(torch.roll(x, 1, 0).cuda().contiguous(), 0.02)
+    assert rel_err(torch.roll(eps2, -1, 0), eps) < 1e-5

@@ -2,12 +2,12 @@
 import pytest
 import torch
 
-from helpers import FORCE_RTOL, MOLS, load, net_params, rel_err, schedule
+from helpers import ALL_MOLS, FORCE_RTOL, MOLS, SHAPES, load, net_params, rel_err, schedule
 from oracle import collapsed_ref, sampler_ref, score_ref
 from oracle.weights import synthetic_net_params
 
 
-@pytest.mark.parametrize("mol", MOLS)
+@pytest.mark.parametrize("mol", ALL_MOLS)
 def test_literal_score_matches_reference(mol):
     p = net_params(mol)
     for c in load(f"score_{mol}.pt")["cases"]:
@@ -18,7 +18,7 @@ def test_literal_score_matches_reference(mol):
         assert rel_err(e, c["energy"]) < 2e-6, (mol, c["t"])
 
 
-@pytest.mark.parametrize("mol", MOLS)
+@pytest.mark.parametrize("mol", ALL_MOLS)
 def test_collapsed_fp64_matches_reference(mol):
     p = net_params(mol)
     for c in load(f"score_{mol}.pt")["cases"][:3]:
@@ -48,7 +48,7 @@ def test_synthetic_weights_through_reference():
         assert rel_err(f64, c["forces"]) < 5e-5, key
 
 
-@pytest.mark.parametrize("mol", MOLS)
+@pytest.mark.parametrize("mol", ALL_MOLS)
 def test_schedule_buffers(mol):
     ck = schedule(mol)
     mine = sampler_ref.cosine_schedule(1000)
@@ -110,3 +110,37 @@ def test_pwd_metric_oracle_matches_reference():
     mx, hists = metrics_ref.pwd_histograms(g["x"], r["gt_max"], g["offset"], g["resolution"])
     assert torch.equal(mx, g["pwd_max"]) and all(torch.equal(a, b) for a, b in zip(hists, g["hists"]))
     assert metrics_ref.pwd_js(g["x"], r["gt_hist"], r["gt_max"], g["offset"], g["resolution"]) == g["js"]
+
+
+def test_all_nine_checkpoints_have_fixtures():
+    """SURVEY 4 tier 1: weights + score / ddpm / langevin fixtures of every shipped checkpoint, with the expected shapes."""
+    import os
+    from helpers import GOLDEN
+    assert len(ALL_MOLS) == 9
+    for mol in ALL_MOLS:
+        for kind in ("weights", "score", "ddpm", "langevin"):
+            assert os.path.exists(os.path.join(GOLDEN, f"{kind}_{mol}.pt")), (kind, mol)
+        p = net_params(mol)
+        N, H, L = SHAPES[mol]
+        assert p["node_embedding.weight"].shape == (H, N + 1) and f"graphtransformer.layers.{L - 1}.0.0.norm.weight" in p
+        assert f"graphtransformer.layers.{L}.0.0.norm.weight" not in p
+
+
+@pytest.mark.parametrize("mol", ("chignolin", "ala2_fold1"))
+def test_long_trajectory_fixture_oracle_vs_reference(mol):
+    """The 250-step reference run (tests/golden/long_<mol>.pt): the literal fp32 oracle reproduces it, and the stored fp64
+    oracle trajectory stays within 3e-6 of the reference at every saved frame -- the dynamics do not amplify rounding
+    differences, which is why the GPU tests use one tolerance for every step count."""
+    g = load(f"long_{mol}.pt")
+    std = g["meta"]["std"]
+    p, sched = net_params(mol), schedule(mol)
+    score = lambda x, tn: score_ref.score_forward(p, x, tn)
+    r = g["runs"][1]                                   # the 50-step Brownian run (cheap on the CPU)
+    c = sampler_ref.langevin_constants(sched, std, r["t"], r["temp"], r["temp"], r["masses"], r["friction"], None)
+    coords, _, _, _ = sampler_ref.langevin_simulate(score, c, r["init_mol"] / std, r["masses"], r["friction"], r["t"], 1000,
+                                                    r["steps"], r["save_interval"], noise=r["noise"])
+    traj = coords.permute(1, 0, 2, 3).reshape(-1, coords.shape[2], 3) * std
+    assert rel_err(traj, r["traj"]) < 1e-5
+    for run in g["runs"]:
+        assert max(run["drift_ref_vs_fp64"]) < 3e-6 and rel_err(run["traj64"], run["traj"]) < 3e-6
+    assert g["chain"]["drift_ref_vs_fp64"] < 1e-5

@@ -3,7 +3,7 @@ import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "two-for-one-diffusion_b200"), os.path.join(ROOT, "tests")]
 import torch
-from helpers import MOLS, load, net_params, rel_err, schedule
+from helpers import ALL_MOLS as MOLS, load, net_params, rel_err, schedule
 from dff_b200 import ScoreEngine, SCHED_KEYS
 from oracle import collapsed_ref, score_ref
 for mol in MOLS:

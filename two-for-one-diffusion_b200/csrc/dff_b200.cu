@@ -415,7 +415,7 @@ int dff_model_create_ex(dff_model_t** out, int device, int num_beads, int hidden
     const bool tc_shape = ((H == 64 && N <= 64) || ((H == 96 || H == 128) && N <= 56));   // shared-memory budget of TcCfg
     if (tc_shape) {
         const int stage_bytes = (HP == 64 ? 4096 : 3072) * 4;            // must equal TcCfg::kStageFloats
-        auto job = [&](int K, int NN, auto&& fill /* (k, n) -> value */, int d_col, uint32_t flags) {
+        auto job = [&](int K, int NN, auto&& fill /* (k, n) -> value */, int d_col, uint32_t flags, int c_col = -1) {
             int KS = 8;
             for (int cand = 8; cand <= K && cand <= 248; cand += 8)
                 if (K % cand == 0 && 2 * cand * NN * 4 <= stage_bytes) KS = cand;
@@ -438,10 +438,12 @@ int dff_model_create_ex(dff_model_t** out, int device, int num_beads, int hidden
             h.j.slice_16b = (uint16_t)((2 * KS * NN * 4) / 16);
             h.j.n_slices = (uint8_t)(K / KS); h.j.ks = (uint8_t)KS; h.j.n = (uint16_t)NN; h.j.d_col = (uint16_t)d_col;
             h.j.flags = (uint8_t)flags;
+            h.j.c_col = (uint16_t)((DFF_TC_SPLIT_ACC && c_col >= 0) ? c_col : d_col);   // correction accumulator (TcCfg::kCorr*)
             tcj.push_back(h);
         };
         using namespace v2;
         const int cD = HP, cA = (int)kColAcc;          // TMEM work area starts after the HP-column block accumulator
+        const int cFF = cD + 256, cOut = HP == 64 ? cD + 384 : -1, cDn = HP == 64 ? cD + 128 + 2 * HP : -1;   // == TcCfg::kCorrFF / kCorrOut / kCorrDn
         const int nch64 = 4 * H / 64;                  // FF hidden chunks of 64 columns; "supers" of <= 4 chunks share the work area
         for (int l = 0; l < L; ++l) {
             const float *Wq = LW(l, 2), *bq = LW(l, 3), *Wkv = LW(l, 4), *bkv = LW(l, 5), *Wo = LW(l, 8), *W1 = LW(l, 13), *W2 = LW(l, 15);
@@ -457,7 +459,7 @@ int dff_model_create_ex(dff_model_t** out, int device, int num_beads, int hidden
             };
             auto outp = [&](int hc) {
                 job(64, HP, [&](int k, int d) -> float { return d < H ? Wo[(size_t)d * 512 + hc * 64 + k] : 0.f; }, cA,
-                    TCJ_SLOT | TCJ_WAIT_POST | (hc > 0 ? TCJ_ACC : 0) | (hc == 7 ? TCJ_COMMIT_ACC : 0));
+                    TCJ_SLOT | TCJ_WAIT_POST | (hc > 0 ? TCJ_ACC : 0) | (hc == 7 ? TCJ_COMMIT_ACC : 0), cOut);
             };
             qkv(0, TCJ_WAIT_POST); qkv(1, 0);
             for (int hc = 0; hc < 8; ++hc) {
@@ -476,7 +478,7 @@ int dff_model_create_ex(dff_model_t** out, int device, int num_beads, int hidden
             }
             for (int c2 = 0; c2 < nch64; ++c2)
                 job(64, HP, [&](int k, int d) -> float { return d < H ? W2[(size_t)d * 4 * H + c2 * 64 + k] : 0.f; }, cA,
-                    TCJ_SLOT | TCJ_WAIT_POST | (c2 > 0 ? TCJ_ACC : 0) | (c2 == nch64 - 1 ? TCJ_COMMIT_ACC : 0));
+                    TCJ_SLOT | TCJ_WAIT_POST | (c2 > 0 ? TCJ_ACC : 0) | (c2 == nch64 - 1 ? TCJ_COMMIT_ACC : 0), cFF);
         }
         tc_njobs_fwd = (int)tcj.size();
         for (int l = L - 1; l >= 0; --l) {
@@ -491,7 +493,7 @@ int dff_model_create_ex(dff_model_t** out, int device, int num_beads, int hidden
             }
             for (int c2 = 0; c2 < nch64; ++c2)
                 job(64, HP, [&](int j, int d) -> float { return d < H ? W1[(size_t)(c2 * 64 + j) * H + d] : 0.f; }, cA,
-                    TCJ_SLOT | TCJ_WAIT_POST | (c2 > 0 ? TCJ_ACC : 0) | (c2 == nch64 - 1 ? TCJ_COMMIT_ACC : 0));
+                    TCJ_SLOT | TCJ_WAIT_POST | (c2 > 0 ? TCJ_ACC : 0) | (c2 == nch64 - 1 ? TCJ_COMMIT_ACC : 0), cFF);
             auto jdo = [&](int hc, uint32_t fl) {
                 job(H, 64, [&](int d, int j) -> float { return Wo[(size_t)d * 512 + hc * 64 + j]; }, cD, TCJ_DBUF | fl);
             };
@@ -502,11 +504,11 @@ int dff_model_create_ex(dff_model_t** out, int device, int num_beads, int hidden
                     // product) that the epilogue adds in fp32: the tensor core's accumulation chain is 192 MMAs long instead of
                     // 576 (its accumulate rounding is what separates this kernel's error from the reference's own)
                     job(64, HP, [&](int j, int d) -> float { return d < H ? Wq[(size_t)(hc * 64 + j) * H + d] : 0.f; }, cA,
-                        TCJ_SLOT | TCJ_WAIT_POST | (hc > 0 ? TCJ_ACC : 0));
+                        TCJ_SLOT | TCJ_WAIT_POST | (hc > 0 ? TCJ_ACC : 0), cDn);
                     job(64, HP, [&](int j, int d) -> float { return d < H ? Wkv[(size_t)(hc * 64 + j) * H + d] : 0.f; }, cD + 128,
-                        TCJ_SLOT | TCJ_WAIT_POST | (hc > 0 ? TCJ_ACC : 0));
+                        TCJ_SLOT | TCJ_WAIT_POST | (hc > 0 ? TCJ_ACC : 0), cDn < 0 ? -1 : cDn + HP);
                     job(64, HP, [&](int j, int d) -> float { return d < H ? Wkv[(size_t)(512 + hc * 64 + j) * H + d] : 0.f; }, cD + 128 + HP,
-                        TCJ_SLOT | TCJ_WAIT_POST | (hc > 0 ? TCJ_ACC : 0) | (hc == 7 ? TCJ_COMMIT_ACC : 0));
+                        TCJ_SLOT | TCJ_WAIT_POST | (hc > 0 ? TCJ_ACC : 0) | (hc == 7 ? TCJ_COMMIT_ACC : 0), cDn < 0 ? -1 : cDn + 2 * HP);
                 }
                 if (hc + 2 < 8) jdo(hc + 2, 0);
             }

@@ -31,6 +31,9 @@ namespace dff {
 namespace v2 {
 
 constexpr int kMmaM = 64;                 // MMA M; a configuration uses kR <= kMmaM node rows per pass
+#ifndef DFF_TC_SPLIT_ACC
+#define DFF_TC_SPLIT_ACC 1      // separate TMEM accumulators for the split-precision correction products of the long K chains
+#endif
 #ifndef DFF_TC_COMPUTE_WARPS
 #define DFF_TC_COMPUTE_WARPS 16
 #endif
@@ -55,7 +58,8 @@ struct TcJob {
     uint16_t n;               // MMA N (64, 128, 192)
     uint16_t d_col;           // TMEM column of D (double-buffered jobs: column of buffer 0)
     uint8_t flags;            // TCJ_*
-    uint8_t pad_[3];
+    uint8_t pad_;
+    uint16_t c_col;           // TMEM column of the correction accumulator (lo*hi + hi*lo); == d_col: none, everything into D
 };
 static_assert(sizeof(TcJob) == 16, "TcJob layout");
 enum : uint32_t {
@@ -96,6 +100,12 @@ struct TcCfg {
     static constexpr int kStages = (HP_ == 64) ? (PN_ > 32 ? 2 : (R_ < 64 && PN_ <= 12 ? 4 : 3)) : (R_ < 64 ? 4 : 3);
     static constexpr int kStageFloats = (kHP == 64) ? 4096 : 3072;
     static constexpr uint32_t kColD = kHP;                   // TMEM work area
+    // Correction accumulators (DFF_TC_SPLIT_ACC): the two small split-precision products of a long K chain accumulate
+    // apart from the hi*hi product, so only K/8 MMAs of the chain round at full magnitude; the epilogue adds the two.
+    static constexpr uint32_t kCorrFF = kColD + 256;         // FF2 / d FF1 chains: right of the <= 256-column super
+    static constexpr bool kCorrAttn = (kHP == 64);           // out-projection and d n_hat chains: only hidden <= 64 has the columns
+    static constexpr uint32_t kCorrOut = kColD + 384;        // right of the double-buffered q|k'|v' accumulators
+    static constexpr uint32_t kCorrDn = kColD + 128 + 2 * kHP;   // three of them, kHP apart, right of the three d n_hat accumulators
     // shared memory carve-up (float offsets)
     static constexpr int oN = 0;                             // [R][LDH] node stream / its gradient (HP = 64 only)
     static constexpr int oQKV = oN + (kNodeInSmem ? kR * LDH : 0);   // [R][LDQ] q|k'|v' of the head chunk; also the [R][LDH] row buffer
@@ -191,16 +201,38 @@ template <int NCOLS, class F>
 __device__ __forceinline__ void tmem_foreach(uint32_t tmem_base, uint32_t col, int rows, F f) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int PARTS = kCW / 4;
-    static_assert(NCOLS % (16 * PARTS) == 0, "column split");
     const int q = warp & 3, part = warp >> 2;
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + col;
     const int row = q * 16 + lane;
     if (q * 16 >= rows) return;                    // warp-uniform: this lane quarter holds no active row
 #pragma unroll 1
-    for (int c = part * (NCOLS / PARTS); c < (part + 1) * (NCOLS / PARTS); c += 16) {
+    for (int c = part * 16; c < NCOLS; c += 16 * PARTS) {      // 16-column chunks round-robin over the warp parts
         float v[16];
         tmem_ld16(taddr + (uint32_t)c, v);
         if (lane < 16 && row < rows) f(row, c, v);
+    }
+}
+// same, D = accumulator at `col` + correction accumulator at `col2` (compile-time switch: SPLIT false -> plain read)
+template <int NCOLS, bool SPLIT, class F>
+__device__ __forceinline__ void tmem_foreach_sum(uint32_t tmem_base, uint32_t col, uint32_t col2, int rows, F f) {
+    if constexpr (!SPLIT) {
+        tmem_foreach<NCOLS>(tmem_base, col, rows, f);
+    } else {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        constexpr int PARTS = kCW / 4;
+        const int q = warp & 3, part = warp >> 2;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+        const int row = q * 16 + lane;
+        if (q * 16 >= rows) return;
+#pragma unroll 1
+        for (int c = part * 16; c < NCOLS; c += 16 * PARTS) {
+            float v[16], w[16];
+            tmem_ld16(lane_base + col + (uint32_t)c, v);
+            tmem_ld16(lane_base + col2 + (uint32_t)c, w);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += w[i];
+            if (lane < 16 && row < rows) f(row, c, v);
+        }
     }
 }
 
@@ -1369,7 +1401,7 @@ __device__ void forward_pass_tc(const ModelDev& M, Ctx2& c, float t_norm) {
         // attention block output -> row buffer; gated residual 1 + LayerNorm 2 -> canonical operand of FF1
         c.acc_wait();
         c.mark(5);
-        tmem_foreach<C::kHP>(c.tmem, kColAcc, rows, [&](int row, int col, const float (&v)[16]) {
+        tmem_foreach_sum<C::kHP, DFF_TC_SPLIT_ACC && C::kCorrAttn>(c.tmem, kColAcc, C::kCorrOut, rows, [&](int row, int col, const float (&v)[16]) {
 #pragma unroll
             for (int i = 0; i < 16; i += 4) {
                 const float4 b = __ldg(reinterpret_cast<const float4*>(W.bo + col + i));
@@ -1429,7 +1461,7 @@ __device__ void forward_pass_tc(const ModelDev& M, Ctx2& c, float t_norm) {
         c.mark(10);
         c.acc_wait();
         c.mark(5);
-        tmem_foreach<C::kHP>(c.tmem, kColAcc, rows, [&](int row, int col, const float (&v)[16]) {
+        tmem_foreach_sum<C::kHP, DFF_TC_SPLIT_ACC != 0>(c.tmem, kColAcc, C::kCorrFF, rows, [&](int row, int col, const float (&v)[16]) {
 #pragma unroll
             for (int i = 0; i < 16; i += 4) {
                 const float4 b = __ldg(reinterpret_cast<const float4*>(W.b2 + col + i));
@@ -1515,7 +1547,7 @@ __device__ void backward_pass_tc(const ModelDev& M, Ctx2& c) {
         c.mark(13);
         c.acc_wait();
         c.mark(5);
-        tmem_foreach<C::kHP>(c.tmem, kColAcc, rows, [&](int row, int col, const float (&v)[16]) {
+        tmem_foreach_sum<C::kHP, DFF_TC_SPLIT_ACC != 0>(c.tmem, kColAcc, C::kCorrFF, rows, [&](int row, int col, const float (&v)[16]) {
 #pragma unroll
             for (int i = 0; i < 16; i += 4)
                 *reinterpret_cast<float4*>(c.sNh + row * C::LDH + col + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
@@ -1572,16 +1604,26 @@ __device__ void backward_pass_tc(const ModelDev& M, Ctx2& c) {
             // d n_hat = (dq Wq) + (dk' Wk) + (dv' Wv): three TMEM accumulators (columns 0, kColD + 128, kColD + 128 + HP), added here
             {
                 const int q = warp_id & 3, part = warp_id >> 2;
-                constexpr int PARTS = kCW / 4, WCOLS = C::kHP / PARTS;
+                constexpr int PARTS = kCW / 4;
                 const int row = q * 16 + lane_id;
                 if (q * 16 < rows) {
                     const uint32_t lane_base = c.tmem + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-                    for (int cc = part * WCOLS; cc < (part + 1) * WCOLS; cc += 16) {
+                    for (int cc = part * 16; cc < C::kHP; cc += 16 * PARTS) {      // 16-column chunks round-robin over the warp parts
                         float v0[16], v1[16], v2[16];
                         tmem_ld16(lane_base + kColAcc + (uint32_t)cc, v0);
                         tmem_ld16(lane_base + C::kColD + 128u + (uint32_t)cc, v1);
                         tmem_ld16(lane_base + C::kColD + 128u + (uint32_t)C::kHP + (uint32_t)cc, v2);
+                        if constexpr (DFF_TC_SPLIT_ACC && C::kCorrAttn) {     // + the three correction accumulators (small terms first)
+                            float w0[16], w1[16];
+                            tmem_ld16(lane_base + C::kCorrDn + (uint32_t)cc, w0);
+                            tmem_ld16(lane_base + C::kCorrDn + (uint32_t)C::kHP + (uint32_t)cc, w1);
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) w0[i] += w1[i];
+                            tmem_ld16(lane_base + C::kCorrDn + 2u * (uint32_t)C::kHP + (uint32_t)cc, w1);
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v0[i] += w0[i] + w1[i];
+                        }
                         if (lane_id < 16 && row < rows) {
 #pragma unroll
                             for (int i = 0; i < 16; i += 4)
@@ -1691,6 +1733,8 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
                     uint32_t dcol = f1 >> 16;
                     const uint32_t a_slot = f2 & TCJ_SLOT, acc_first = (f2 & TCJ_ACC) ? 1u : 0u, wait_post = f2 & TCJ_WAIT_POST, dbuf = f2 & TCJ_DBUF;
                     const uint32_t commit_acc = f2 & TCJ_COMMIT_ACC, commit_d1 = f2 & TCJ_COMMIT_D1;
+                    const uint32_t ccol = f2 >> 16;
+                    const bool split = ccol != dcol;                 // never set on double-buffered jobs
                     if (wait_post) {
                         ++post_seq;
                         TCP_BEGIN(); spin_until(ctr, post_seq, 7); TCP_END(iw, 0);
@@ -1704,6 +1748,7 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
                     uint64_t dal = kDescA | (uint64_t)(((a_slot ? slot_lo_a : nhat_lo_a) >> 4) & 0x3FFFu);
                     const uint32_t idesc = tc::idesc_tf32(64, (int)n);
                     const uint32_t d_tmem = tmem + dcol;
+                    const uint32_t c_tmem = split ? tmem + ccol : d_tmem;    // lo*hi and hi*lo go here
                     const uint64_t descB = kDescHi | ((uint64_t)n << 16);                          // LBO = n * 16 B
                     const uint32_t b_step = 2u * n;                                               // (2 * n * 16 B) >> 4
                     const uint32_t lo_off = (ks * n * 4u) >> 4;                                   // lo image follows the hi image
@@ -1716,16 +1761,16 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
                         { TCP_BEGIN(); mbar_wait_wd(bars + B_FULL + stg, use & 1u, 6); TCP_END(iw, 2); }
                         tc::fence_after_sync();
                         if (tc::elect_one()) {
-                            tc::mma_tf32_ss(d_tmem, dal, dbh, idesc, acc);          // first k-step of the slice (may overwrite D)
-                            tc::mma_tf32_acc(d_tmem, dah, dbl, idesc);
-                            tc::mma_tf32_acc(d_tmem, dah, dbh, idesc);
+                            tc::mma_tf32_ss(c_tmem, dal, dbh, idesc, acc);          // first k-step of the slice (may overwrite D)
+                            tc::mma_tf32_acc(c_tmem, dah, dbl, idesc);
+                            tc::mma_tf32_ss(d_tmem, dah, dbh, idesc, split ? acc : 1u);
                         }
                         acc = 1u;
                         for (uint32_t kk = 1; kk < ksteps; ++kk) {
                             dah += a_step; dal += a_step; dbh += b_step; dbl += b_step;
                             if (tc::elect_one()) {
-                                tc::mma_tf32_acc(d_tmem, dal, dbh, idesc);
-                                tc::mma_tf32_acc(d_tmem, dah, dbl, idesc);
+                                tc::mma_tf32_acc(c_tmem, dal, dbh, idesc);
+                                tc::mma_tf32_acc(c_tmem, dah, dbl, idesc);
                                 tc::mma_tf32_acc(d_tmem, dah, dbh, idesc);
                             }
                         }

@@ -164,7 +164,14 @@ class Langevin:
         if sub_interval % self.save_interval != 0:
             raise ValueError("The save_interval must be a factor of the simulated interval")
         B, N, si = self.n_sims, self.n_beads, self.save_interval
-        n_save = sub_interval // si
+        done_before = getattr(self, "t", 0)
+        # frames this call can still produce: the loop stops at self.length, so never allocate (and return) more than that
+        n_save = min(sub_interval, max(self.length - done_before, 0)) // si
+        if n_save == 0 and hasattr(self, "x_old"):          # the run is complete: nothing to integrate, no RNG draws
+            self.simulated_coords = np.zeros((B, 0, N, 3), dtype=np.float32)
+            if self.friction is not None:
+                self.kinetic_energies = np.zeros((B, 0), dtype=np.float32)
+            return self.simulated_coords
         eng = self.model.model_gnn.engine(B)
         dev = eng.device
         if not hasattr(self, "x_old"):
@@ -181,7 +188,7 @@ class Langevin:
         coords_h = torch.empty(n_save, B, N, 3).pin_memory()
         copy_stream = torch.cuda.Stream(device=dev)
         use_host_rng = self.rng_mode != "philox"
-        if use_host_rng:
+        if use_host_rng and n_save > 0:
             stage = [torch.empty(si, B, N, 3).pin_memory() for _ in range(2)]
             noise_d = [torch.empty(si, B, N, 3, device=dev) for _ in range(2)]
             ready = [torch.cuda.Event() for _ in range(2)]

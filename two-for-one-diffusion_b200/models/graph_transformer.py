@@ -102,20 +102,44 @@ class GraphTransformer(nn.Module):
 
     @staticmethod
     def _shared_t(t) -> float:
+        """The kernel evaluates one noise level per call (every caller on the sampling path passes a uniform t:
+        ddpm.py:240-247, langevin.py:77); the reference embeds t per sample (graph_transformer.py:91), so a
+        non-uniform t would silently give different numbers -- refuse it instead."""
         if torch.is_tensor(t):
             flat = t.reshape(-1)
+            if flat.numel() == 0:
+                raise DffError("t is empty")
+            if flat.numel() > 1 and not bool((flat == flat[0]).all()):
+                raise DffError("GraphTransformer.forward on B200 needs the same t for the whole batch "
+                               "(per-sample noise levels are a training-path feature: split the batch by t)")
             return float(flat[0])
         return float(t)
+
+    def _check_h(self, h):
+        """`h` must be the bead one-hot matrix the node embedding was folded with (graph_transformer.py:99-103 with
+        trainset.bead_onehot = eye(N)); any other feature matrix would silently be ignored."""
+        if h is None:
+            return
+        if tuple(h.shape) != (self.num_beads, self.num_beads):
+            raise DffError(f"h must be the [{self.num_beads},{self.num_beads}] bead one-hot matrix")
+        key = (h.data_ptr(), h._version, str(h.device))
+        if getattr(self, "_h_ok", None) != key:
+            if not bool((h.detach().to("cpu", torch.float32) == torch.eye(self.num_beads)).all()):
+                raise DffError("h must be the identity bead one-hot matrix (trainset.bead_onehot); other node features "
+                               "are not supported by the fused kernel")
+            self._h_ok = key
 
     def forward(self, x, h, t, return_energy=False, alphas: Optional[torch.Tensor] = None):
         """x [B,N,3]; h [N,N] bead one-hot (identity); t [B] / [B,1,1] = step/T shared by the batch.
         Returns forces (= -dE/dx, the epsilon prediction) [B,N,3], or energies [B,N,1] if return_energy.
         `alphas` is accepted and unused, exactly like the reference (graph_transformer.py:83)."""
-        if h is not None and tuple(h.shape) != (self.num_beads, self.num_beads):
-            raise DffError(f"h must be the [{self.num_beads},{self.num_beads}] bead one-hot matrix")
+        self._check_h(h)
+        t_shared = self._shared_t(t)
+        if torch.is_tensor(t) and t.reshape(-1).numel() not in (1, x.shape[0]):
+            raise DffError(f"t has {t.reshape(-1).numel()} entries for a batch of {x.shape[0]}")
         eng = self.engine(x.shape[0])
         xin = x.detach().to(eng.device, torch.float32).contiguous()
         if not self.conservative:       # the decoder output is the prediction; return_energy is ignored (:107-113)
-            return eng.score(xin, self._shared_t(t), want_forces=True, want_energy=False)[0]
-        eps, en = eng.score(xin, self._shared_t(t), want_forces=not return_energy, want_energy=return_energy)
+            return eng.score(xin, t_shared, want_forces=True, want_energy=False)[0]
+        eps, en = eng.score(xin, t_shared, want_forces=not return_energy, want_energy=return_energy)
         return en.unsqueeze(-1) if return_energy else eps
