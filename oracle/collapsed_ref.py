@@ -30,7 +30,8 @@ SCALE = DIM_HEAD ** -0.5
 
 
 def fold_edge_path(p: Dict[str, torch.Tensor], l: int):
-    """A = W_ekv W_e  [512,E],  c = W_ekv b_e + b_ekv  [512]  (computed in fp64, cast back)."""
+    """A = W_ekv W_e  [512,E],  c = W_ekv b_e + b_ekv  [512]  (computed in fp64, cast back).
+    E = 3 (intrinsic), 1 (squared distance, or the all-zero placeholder feature), 4 (intrinsic | squared distance)."""
     pre = f"graphtransformer.layers.{l}.0.0.fn."
     Wekv = p[pre + "edges_to_kv.weight"].double()
     A = Wekv @ p["edge_embedding.weight"].double()
@@ -90,15 +91,36 @@ def _unheads(t):        # [B,8,N,64] -> [B,N,512]
 
 def node_embedding0(p, N: int, t_norm: float, dtype):
     """Layer-0 node stream: W_n [onehot_i, t] + b_n  -- independent of x and of the sample
-    (graph_transformer.py:99-103 with h = eye(N))."""
+    (graph_transformer.py:99-103 with h = eye(N)).  With use_abs_coords the input row is [onehot_i, x_i, t]
+    (graph_transformer.py:99-100): the x part is added by the caller."""
     Wn = p["node_embedding.weight"].to(dtype)
-    return Wn[:, :N].t() + Wn[:, N] * t_norm + p["node_embedding.bias"].to(dtype)     # [N,H]
+    return Wn[:, :N].t() + Wn[:, -1] * t_norm + p["node_embedding.bias"].to(dtype)     # [N,H]
+
+
+def split_edge_map(A_full: torch.Tensor, use_intrinsic: bool, use_distances: bool):
+    """Folded edge map columns -> (A [512,3] acting on x_j - x_i, a [512] acting on |x_j - x_i|^2)
+    (graph_transformer.py:116-140: features are diff (3), dist (1), cat(diff, dist) (4) or zeros (1))."""
+    z3 = torch.zeros(A_full.shape[0], 3, dtype=A_full.dtype)
+    z1 = torch.zeros(A_full.shape[0], dtype=A_full.dtype)
+    if use_intrinsic and use_distances:
+        return A_full[:, :3], A_full[:, 3]
+    if use_intrinsic:
+        return A_full[:, :3], z1
+    if use_distances:
+        return z3, A_full[:, 0]
+    return z3, z1
 
 
 def forward_backward(p: Dict[str, torch.Tensor], x: torch.Tensor, t_norm: float,
-                     want_stash: bool = False):
+                     want_stash: bool = False, *, use_intrinsic_coords: bool = True, use_abs_coords: bool = False,
+                     use_distances: bool = False):
     """x [B,N,3] (any float dtype; centred internally), t_norm python float.
-    Returns (forces [B,N,3], energy [B,N], stash or None)."""
+    Returns (forces [B,N,3], energy [B,N], stash or None).
+
+    Edge modes (graph_transformer.py:116-140), all collapsed exactly:  e_ij = A (x_j - x_i) + a |x_j - x_i|^2 + c
+      logits_ij = s (q_i . k_j + u_i . x_j + alpha_i D2_ij),   u_i = A_h^T q_i,  alpha_i = a_h . q_i,  D2_ij = |x_i - x_j|^2
+      o_i       = sum_j p_ij v_j + A_h (xbar_i - x_i) + c_h + a_h z_i,   z_i = sum_j p_ij D2_ij
+    use_abs_coords adds W_n[:, N:N+3] x_i to the layer-0 node stream, which makes layer 0 x-dependent."""
     dtype = x.dtype
     p = {k: v.to(dtype) for k, v in p.items()}
     x = x - x.mean(dim=1, keepdim=True)
@@ -106,12 +128,19 @@ def forward_backward(p: Dict[str, torch.Tensor], x: torch.Tensor, t_norm: float,
     L = num_layers(p)
     H = p["node_embedding.weight"].shape[0]
     nodes = node_embedding0(p, N, float(t_norm), dtype).unsqueeze(0).expand(B, N, H)
+    Wnx = None
+    if use_abs_coords:
+        Wnx = p["node_embedding.weight"][:, N:N + 3]                        # [H,3]
+        nodes = nodes + x @ Wnx.t()
+    D2 = ((x[:, :, None, :] - x[:, None, :, :]) ** 2).sum(-1)                 # [B,N,N]
     saved = []
     for l in range(L):
         a_ = f"graphtransformer.layers.{l}.0."
         f_ = f"graphtransformer.layers.{l}.1."
-        A, c = fold_edge_path(p, l)
+        A_full, c = fold_edge_path(p, l)
+        A, a = split_edge_map(A_full, use_intrinsic_coords, use_distances)
         Ah = A.reshape(HEADS, DIM_HEAD, 3)
+        ah = a.reshape(HEADS, DIM_HEAD)
         ch = c.reshape(HEADS, DIM_HEAD)
         n_in = nodes
         nh, y1, r1 = _ln_fwd(n_in, p[a_ + "0.norm.weight"], p[a_ + "0.norm.bias"])
@@ -120,29 +149,33 @@ def forward_backward(p: Dict[str, torch.Tensor], x: torch.Tensor, t_norm: float,
         k, v = kv[..., :INNER], kv[..., INNER:]
         qh, kh, vh = _heads(q), _heads(k), _heads(v)
         u = torch.einsum("bhid,hdc->bhic", qh, Ah)                          # [B,8,N,3]
-        logits = SCALE * (qh @ kh.transpose(-1, -2) + torch.einsum("bhic,bjc->bhij", u, x))
+        alpha = torch.einsum("bhid,hd->bhi", qh, ah)                        # [B,8,N]
+        logits = SCALE * (qh @ kh.transpose(-1, -2) + torch.einsum("bhic,bjc->bhij", u, x) + alpha[..., None] * D2[:, None])
         pr = logits.softmax(-1)                                             # [B,8,N,N]
         xbar = torch.einsum("bhij,bjc->bhic", pr, x)
-        oh = pr @ vh + torch.einsum("hdc,bhic->bhid", Ah, xbar - x[:, None]) + ch[None, :, None, :]
+        z = (pr * D2[:, None]).sum(-1)                                      # [B,8,N]
+        oh = pr @ vh + torch.einsum("hdc,bhic->bhid", Ah, xbar - x[:, None]) + ch[None, :, None, :] \
+            + z[..., None] * ah[None, :, None, :]
         att = _unheads(oh) @ p[a_ + "0.fn.to_out.weight"].t() + p[a_ + "0.fn.to_out.bias"]
         m, g1 = _gate_fwd(p[a_ + "1.proj.0.weight"], att, n_in)
         mh, y2, r2 = _ln_fwd(m, p[f_ + "0.norm.weight"], p[f_ + "0.norm.bias"])
         h1 = mh @ p[f_ + "0.fn.0.weight"].t() + p[f_ + "0.fn.0.bias"]
         ff = _gelu(h1) @ p[f_ + "0.fn.2.weight"].t() + p[f_ + "0.fn.2.bias"]
         nodes, g2 = _gate_fwd(p[f_ + "1.proj.0.weight"], ff, m)
-        saved.append(dict(n_in=n_in, y1=y1, r1=r1, q=q, k=k, v=v, u=u, p=pr, att=att, g1=g1, m=m,
-                          y2=y2, r2=r2, h1=h1, ff=ff, g2=g2, Ah=Ah, out=nodes))
+        saved.append(dict(n_in=n_in, y1=y1, r1=r1, q=q, k=k, v=v, u=u, alpha=alpha, z=z, p=pr, att=att, g1=g1, m=m,
+                          y2=y2, r2=r2, h1=h1, ff=ff, g2=g2, Ah=Ah, ah=ah, out=nodes))
     wd = p["node_decoder.weight"][0]
     energy = nodes @ wd + p["node_decoder.bias"][0]                          # [B,N]
 
     # ---- reverse mode w.r.t. x (d sum(E)) ----
     dn = wd.expand(B, N, H).clone()
     dx = torch.zeros_like(x)
+    xd = x[:, :, None, :] - x[:, None, :, :]                                  # [B,i,j,3] = x_i - x_j
     for l in reversed(range(L)):
         a_ = f"graphtransformer.layers.{l}.0."
         f_ = f"graphtransformer.layers.{l}.1."
         s = saved[l]
-        Ah = s["Ah"]
+        Ah, ah = s["Ah"], s["ah"]
         dff, dm = _gate_bwd(p[f_ + "1.proj.0.weight"], s["ff"], s["m"], s["g2"], dn)
         dact = dff @ p[f_ + "0.fn.2.weight"]
         dh1 = dact * _gelu_grad(s["h1"])
@@ -152,19 +185,26 @@ def forward_backward(p: Dict[str, torch.Tensor], x: torch.Tensor, t_norm: float,
         do = _heads(datt @ p[a_ + "0.fn.to_out.weight"])                    # [B,8,N,64]
         qh, kh, vh = _heads(s["q"]), _heads(s["k"]), _heads(s["v"])
         w = torch.einsum("bhid,hdc->bhic", do, Ah)                          # [B,8,N,3]
-        dp = do @ vh.transpose(-1, -2) + torch.einsum("bhic,bjc->bhij", w, x)
+        beta = torch.einsum("bhid,hd->bhi", do, ah)                         # [B,8,N]   d / d z_i
+        dp = do @ vh.transpose(-1, -2) + torch.einsum("bhic,bjc->bhij", w, x) + beta[..., None] * D2[:, None]
         ds = s["p"] * (dp - (s["p"] * dp).sum(-1, keepdim=True))
         dx = dx + torch.einsum("bhij,bhic->bjc", s["p"], w) \
                 + SCALE * torch.einsum("bhij,bhic->bjc", ds, s["u"]) - w.sum(1)
-        if l == 0:
+        # squared-distance channel: E_ij = d / d D2_ij ;  d D2_ij / d x_i = 2 (x_i - x_j) = - d D2_ij / d x_j
+        E = (SCALE * ds * s["alpha"][..., None] + s["p"] * beta[..., None]).sum(1)      # [B,i,j]
+        dx = dx + 2 * torch.einsum("bij,bijc->bic", E, xd) - 2 * torch.einsum("bij,bijc->bjc", E, xd)
+        if l == 0 and not use_abs_coords:
             s["do"], s["ds"], s["w"] = do, ds, w
             break                                                           # layer-0 nodes do not depend on x
         dsx = torch.einsum("bhij,bjc->bhic", ds, x)
-        dq = SCALE * (ds @ kh + torch.einsum("hdc,bhic->bhid", Ah, dsx))
+        dalpha = SCALE * (ds * D2[:, None]).sum(-1)                         # [B,8,N]
+        dq = SCALE * (ds @ kh + torch.einsum("hdc,bhic->bhid", Ah, dsx)) + dalpha[..., None] * ah[None, :, None, :]
         dk = SCALE * (ds.transpose(-1, -2) @ qh)
         dv = s["p"].transpose(-1, -2) @ do
         dnh = _unheads(dq) @ p[a_ + "0.fn.to_q.weight"] \
             + torch.cat([_unheads(dk), _unheads(dv)], -1) @ p[a_ + "0.fn.to_kv.weight"]
         dn = dn_res + _ln_bwd(dnh, s["y1"], s["r1"], p[a_ + "0.norm.weight"])
         s["do"], s["ds"], s["w"], s["dq"], s["dk"], s["dv"], s["dn_in"] = do, ds, w, dq, dk, dv, dn
+    if use_abs_coords:
+        dx = dx + dn @ Wnx                                                  # node_embedding's x columns
     return -dx, energy, (saved if want_stash else None)

@@ -63,7 +63,7 @@ def _edge_features(x: torch.Tensor, use_intrinsic: bool, use_dist: bool) -> torc
     # graph_transformer.py:116-140; diff[b,i,j] = x[b,j] - x[b,i]
     B, N, _ = x.shape
     if not use_intrinsic and not use_dist:
-        return torch.zeros(B, N, N, 1, dtype=x.dtype)
+        return torch.zeros(B, N, N, 1, dtype=x.dtype, device=x.device)
     diff = x[:, None, :, :] - x[:, :, None, :]
     if use_intrinsic and not use_dist:
         return diff
@@ -134,12 +134,12 @@ def score_forward(p: Dict[str, torch.Tensor], x: torch.Tensor, t_norm, *,
     B, N, _ = x.shape
     dtype = x.dtype
     if h is None:
-        h = torch.eye(N, dtype=dtype)
-    t = torch.as_tensor(t_norm, dtype=dtype).reshape(-1, 1, 1)
+        h = torch.eye(N, dtype=dtype, device=x.device)
+    t = torch.as_tensor(t_norm, dtype=dtype).to(x.device).reshape(-1, 1, 1)
     if t.shape[0] == 1:
         t = t.expand(B, 1, 1)
     t = t.repeat(1, N, 1)
-    hb = h.to(dtype).unsqueeze(0).repeat(B, 1, 1)
+    hb = h.to(x.device, dtype).unsqueeze(0).repeat(B, 1, 1)
     with torch.enable_grad() if conservative else torch.no_grad():
         if conservative:
             x = x.requires_grad_(True)

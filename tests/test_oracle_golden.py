@@ -144,3 +144,22 @@ def test_long_trajectory_fixture_oracle_vs_reference(mol):
     for run in g["runs"]:
         assert max(run["drift_ref_vs_fp64"]) < 3e-6 and rel_err(run["traj64"], run["traj"]) < 3e-6
     assert g["chain"]["drift_ref_vs_fp64"] < 1e-5
+
+
+def test_edge_modes_oracle_matches_reference():
+    """every combination of use_intrinsic_coords / use_distances / use_abs_coords, conservative and not
+    (tests/golden/score_edge_modes.pt, outputs of the unmodified reference on seeded weights): the literal oracle reproduces
+    them to fp32 noise and the collapsed fp64 oracle (the formulation the kernel executes) agrees to the reference's own
+    fp32-vs-fp64 gap."""
+    g = load("score_edge_modes.pt")
+    assert len(g) == 25
+    for key, c in g.items():
+        p = synthetic_net_params(c["N"], c["H"], c["L"], c["seed"], in_edge=c["in_edge"], in_node_extra=3 if c["use_abs_coords"] else 0,
+                                 out_dim=1 if c["conservative"] else 3)
+        kw = dict(use_intrinsic_coords=c["use_intrinsic_coords"], use_distances=c["use_distances"], use_abs_coords=c["use_abs_coords"])
+        f = score_ref.score_forward(p, c["x"], c["t_norm"], **kw)
+        assert rel_err(f, c["forces"]) < 5e-6, (key, rel_err(f, c["forces"]))
+        if c["conservative"]:
+            f64, e64, _ = collapsed_ref.forward_backward(score_ref.to_dtype(p, torch.float64), c["x"].double(), c["t_norm"], **kw)
+            assert rel_err(f64, c["forces"]) < 5e-5, (key, rel_err(f64, c["forces"]))
+            assert rel_err(e64, c["energy"]) < 5e-5, (key, rel_err(e64, c["energy"]))

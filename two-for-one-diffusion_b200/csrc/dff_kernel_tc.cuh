@@ -515,6 +515,17 @@ __device__ __forceinline__ void ln_backward_rows_tc(float* sN, const float* sD, 
     }
 }
 
+// ------------------------------------------------------------------ attention contractions: warp-level tensor-core tiles
+#ifndef DFF_TC_ATTN_SIMT
+#define DFF_TC_ATTN_SIMT 0      // 1: the round-1 CUDA-core attention routines (A/B reference builds only)
+#endif
+}  // namespace v2
+}  // namespace dff
+#include "dff_attn_mma.cuh"
+namespace dff {
+namespace v2 {
+
+#if DFF_TC_ATTN_SIMT
 // ------------------------------------------------------------------ row-local attention (a group of LPR lanes owns one node row)
 // LPR = 16 lanes per row for N <= 16 beads (two rows per warp), 32 for N <= 32.  Inside a group the lane index is the key
 // index j while logits / probabilities are formed and the output-column group (DPL = 64 / LPR columns) while values are
@@ -1335,6 +1346,8 @@ __device__ __forceinline__ void attn_backward_dkv_quads(Ctx2& c, const LayerDev&
     }
 }
 
+#endif  // DFF_TC_ATTN_SIMT
+
 // FF hidden block [rows][4H] TMEM -> shared (row stride LDF), so that the GELU phases can be spread over all threads
 constexpr int kLDF = 256 + 4;
 
@@ -1386,14 +1399,30 @@ __device__ void forward_pass_tc(const ModelDev& M, Ctx2& c, float t_norm) {
                 }
                 c.mark(2);
             }
+#if DFF_TC_ATTN_SIMT
             // logits, softmax, P V' - A x_i + c -> canonical operand of the out-projection (row-local, no barrier inside)
-            bool done_q = false;
-            {
-                if (c.quads) { attn_forward_quads<C>(c, W, hc, N, NP, st + M.off[ST_P] + (size_t)hc * R * NP); done_q = true; }
-            }
-            if (done_q) { }
+            if (c.quads) attn_forward_quads<C>(c, W, hc, N, NP, st + M.off[ST_P] + (size_t)hc * R * NP);
             else if (c.pairs) attn_forward_pairs<C>(c, W, hc, N, NP, st + M.off[ST_P] + (size_t)hc * R * NP);
             else attn_forward_rows<C>(c, W, hc, N, NP, st + M.off[ST_P] + (size_t)hc * R * NP);
+#else
+            {   // logits (HMMA tiles) -> softmax (row-local) -> P V' - A x_i + c (HMMA tiles) -> canonical operand of the out-projection
+                const AttnGeo G(N, NP, c.S_act);
+                attn_logits_mma<C>(c.sQKV, c.sP, G);
+                csync();
+                attn_softmax_rows(c.sP, st + M.off[ST_P] + (size_t)hc * R * NP, G);
+                csync();
+                attn_weighted_mma<C>(c.sP, c.sQKV, C::LDQ, 128, G, [&](int row, int col, float v0, float v1) {
+                    const int gc = hc * 64 + col;
+                    const float2 cv = __ldg(reinterpret_cast<const float2*>(W.cvec + gc));
+                    const float4 e0 = __ldg(reinterpret_cast<const float4*>(W.A + gc * 4)), e1 = __ldg(reinterpret_cast<const float4*>(W.A + gc * 4 + 4));
+                    const float x0 = c.sX[row * 4], x1 = c.sX[row * 4 + 1], x2 = c.sX[row * 4 + 2];
+                    v0 += cv.x - (e0.x * x0 + e0.y * x1 + e0.z * x2);
+                    v1 += cv.y - (e1.x * x0 + e1.y * x1 + e1.z * x2);
+                    c.slot_acquire();      // the previous out-projection has had the whole head to finish reading the slot
+                    can_store2<C::kCS>(c.slot_hi, c.slot_lo, row, col, v0, v1);
+                });
+            }
+#endif
             c.mark(3);
             c.slot_post();
             c.mark(4);
@@ -1584,11 +1613,8 @@ __device__ void backward_pass_tc(const ModelDev& M, Ctx2& c) {
                 c.dq_release();
                 c.mark(16);
             }
-            bool done_q = false;
-            {
-                if (c.quads) { attn_backward_ds_dq_quads<C>(c, N, NP, l > 0); done_q = true; }
-            }
-            if (done_q) { }
+#if DFF_TC_ATTN_SIMT
+            if (c.quads) attn_backward_ds_dq_quads<C>(c, N, NP, l > 0);
             else if (c.pairs) attn_backward_ds_dq_pairs<C>(c, N, NP, l > 0);
             else attn_backward_ds_dq<C>(c, N, NP, l > 0);
             c.mark(17);
@@ -1598,6 +1624,29 @@ __device__ void backward_pass_tc(const ModelDev& M, Ctx2& c) {
             else if (c.pairs) attn_backward_dkv_pairs<C>(c, W, hc, N, NP, l > 0);
             else attn_backward_dkv<C>(c, W, hc, N, NP, l > 0);
             c.mark(19);
+#else
+            {
+                const AttnGeo G(N, NP, c.S_act);
+                attn_dp_uw_mma<C>(c.sQKV, c.sO, c.sDS, W.A, hc, G);       // dp, u = A^T q, w = A^T do (HMMA tiles)
+                csync();
+                attn_ds_rows(c.sP, c.sDS, G);
+                csync();
+                c.mark(17);
+                attn_dx_rows<C>(c.sQKV, c.sO, c.sP, c.sDS, c.sDX, G);     // dx from p, ds, u, w: no dk' / dv' needed
+                if (l > 0) {
+                    attn_grad_to_slot_mma<C, false>(c, c.sDS, c.sQKV, C::LDQ, 64, kAttnScale, G);     // dq  -> job d q
+                    c.slot_post();
+                    c.mark(18);
+                    attn_grad_to_slot_mma<C, true>(c, c.sDS, c.sQKV, C::LDQ, 0, kAttnScale, G);       // dk' -> job d k'
+                    c.slot_post();
+                    attn_grad_to_slot_mma<C, true>(c, c.sP, c.sO, C::LDO, 0, 1.0f, G);                // dv' -> job d v'
+                    c.slot_post();
+                } else {
+                    csync();          // the next head reloads the buffers
+                }
+                c.mark(19);
+            }
+#endif
         }
         if (l > 0) {
             c.acc_wait();
@@ -1819,6 +1868,7 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
             c.S_act = my_n / my_groups + (g < my_n % my_groups ? 1 : 0);
             s_next += c.S_act;
             c.rows_act = c.S_act * N;
+#if DFF_TC_ATTN_SIMT
 #ifndef DFF_TC_QUADS16
 #define DFF_TC_QUADS16 0
 #endif
@@ -1828,6 +1878,9 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
             c.pairs = true;
 #else
             c.pairs = c.rows_act > kCW * AttnMap<C>::UPW;
+#endif
+#else
+            c.quads = c.pairs = false;
 #endif
             for (int idx = tid; idx < R * 3; idx += kCT) {
                 const int r = idx / 3, cc = idx - r * 3;
