@@ -1,0 +1,10 @@
+#!/bin/bash
+# developer aid (GPU box): parity tests + short benches (headline only) for build variants, then the per-phase profile
+for v in "$@"; do
+  export DFF_LIB_PATH=$PWD/two-for-one-diffusion_b200/dff_b200/libdff_v$v.so
+  echo "=== variant $v"
+  timeout 900 python -m pytest tests/test_gpu_score.py tests/test_gpu_samplers.py -m gpu -x -q 2>&1 | tail -14
+  for w in c2 c3 c4 c5; do timeout 300 python bench.py --workload $w --steps 3 --headline-only 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('   ', d['config']['workload'][:18], round(d['md_steps_per_s'],1), 'steps/s', round(d['roofline']['achieved'],2), 'TF/s')"; done
+done
+unset DFF_LIB_PATH
+bash tools/tc_prof2.sh

@@ -23,6 +23,13 @@ __global__ void k(float* out, long long* cyc, int iters) {
 }
 int main() {
     float* out; long long* cyc; cudaMalloc(&out, 148 * 1024 * 4); cudaMalloc(&cyc, 148 * 8);
+    for (int acc : {1, 2, 3}) {      // dependent-chain latency: one warp, `acc` independent accumulators
+        const int iters = 4000;
+        if (acc == 1) k<1><<<1, 32>>>(out, cyc, iters); else if (acc == 2) k<2><<<1, 32>>>(out, cyc, iters); else k<3><<<1, 32>>>(out, cyc, iters);
+        cudaDeviceSynchronize();
+        long long h0; cudaMemcpy(&h0, cyc, 8, cudaMemcpyDeviceToHost);
+        printf("1 warp, %d accumulator chain(s): %.1f cycles per HMMA issue slot\n", acc, (double)h0 / (iters * acc));
+    }
     for (int warps : {1, 4, 8, 16, 32}) {
         const int iters = 2000;
         k<8><<<148, warps * 32>>>(out, cyc, iters); cudaDeviceSynchronize();

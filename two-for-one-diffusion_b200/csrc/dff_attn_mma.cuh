@@ -6,8 +6,8 @@
 //             dx_j += sum_i (p_ij w_i + s ds_ij u_i) - w_j      with  u_i = A_h^T q_i,  w_i = A_h^T do_i   
 //
 // Attention is block diagonal: a 64-row tile holds S_act samples of N beads and a query only sees the keys of its own
-// sample.  Every contraction is therefore cut into 16 x 8 output tiles per (sample, 16-row block, 8-column block) and
-// spread over the 16 compute warps; a tile is a chain of `mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32` (SASS HMMA.1688.F32.TF32)
+// sample.  Every contraction is therefore cut into 16 x 16 output blocks per (sample, 16-row block, pair of 8-column tiles) and
+// spread over the 16 compute warps; a block is two chains of `mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32` (SASS HMMA.1688.F32.TF32)
 // with the 3xTF32 split done in registers (lo*hi + hi*lo + hi*hi, fp32 accumulate), operands read straight from the
 // row-major fp32 shared-memory buffers the TMEM epilogues fill -- no layout change, no extra shared memory, no TMEM.
 // Why warp-level MMA and not tcgen05 here (measured, profiles/r02/hmma_rate.txt): mma.sync TF32 sustains 512 MAC/cycle/SM,
@@ -36,128 +36,182 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
     lo = __float_as_uint(x - __uint_as_float(hi));
 }
 // C[16 x 8] += A[16 x 8 ksteps] * B[8 ksteps x 8]  at fp32 grade.  la(kk, a[4]) / lb(kk, b[2]) fill the fp32 fragments of k-step kk.
+// The three split products accumulate in three independent register accumulators (three dependent HMMA chains of length
+// `ksteps` instead of one of length 3 * ksteps; the two small products are summed first), and the fragments of two k-steps
+// are loaded before their six HMMAs are issued.
 template <class LA, class LB>
 __device__ __forceinline__ void tile_mma(float (&c)[4], int ksteps, LA la, LB lb) {
-#pragma unroll 2
-    for (int kk = 0; kk < ksteps; ++kk) {
-        float a[4], b[2];
-        la(kk, a);
-        lb(kk, b);
+    float clh[4] = {0.f, 0.f, 0.f, 0.f}, chl[4] = {0.f, 0.f, 0.f, 0.f};
+    int kk = 0;
+    for (; kk + 1 < ksteps; kk += 2) {
+        float a0[4], b0[2], a1[4], b1[2];
+        la(kk, a0); lb(kk, b0); la(kk + 1, a1); lb(kk + 1, b1);
+        uint32_t ah[4], al[4], bh[2], bl[2], ah1[4], al1[4], bh1[2], bl1[2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { split_tf32(a0[i], ah[i], al[i]); split_tf32(a1[i], ah1[i], al1[i]); }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) { split_tf32(b0[i], bh[i], bl[i]); split_tf32(b1[i], bh1[i], bl1[i]); }
+        hmma_tf32(clh, al, bh); hmma_tf32(chl, ah, bl); hmma_tf32(c, ah, bh);
+        hmma_tf32(clh, al1, bh1); hmma_tf32(chl, ah1, bl1); hmma_tf32(c, ah1, bh1);
+    }
+    if (kk < ksteps) {
+        float a0[4], b0[2];
+        la(kk, a0); lb(kk, b0);
         uint32_t ah[4], al[4], bh[2], bl[2];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) split_tf32(a[i], ah[i], al[i]);
+        for (int i = 0; i < 4; ++i) split_tf32(a0[i], ah[i], al[i]);
 #pragma unroll
-        for (int i = 0; i < 2; ++i) split_tf32(b[i], bh[i], bl[i]);
-        hmma_tf32(c, al, bh);
-        hmma_tf32(c, ah, bl);
-        hmma_tf32(c, ah, bh);
+        for (int i = 0; i < 2; ++i) split_tf32(b0[i], bh[i], bl[i]);
+        hmma_tf32(clh, al, bh); hmma_tf32(chl, ah, bl); hmma_tf32(c, ah, bh);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c[i] += clh[i] + chl[i];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Work decomposition.  An ITEM is (sample, 16-row block, pair of 8-column tiles) of one product; the items of a phase are
+// dealt round-robin to the 16 compute warps.  Phases of one head (CTA-wide barriers between them):
+//   forward : [logits items] | [softmax rows] | [P V' items -> slot]
+//   reverse : [dp items + u / w items] | [ds rows] | [dx rows, dq items -> slot] | [dk' items -> slot] | [dv' items -> slot]
+struct AttnGeo {
+    int N, NP, S_act, MB, NK, NKP;      // beads, beads padded to 4, samples, row blocks / key tiles / key-tile pairs per sample
+    __device__ __forceinline__ AttnGeo(int N_, int NP_, int S_) : N(N_), NP(NP_), S_act(S_), MB((N_ + 15) >> 4), NK((N_ + 7) >> 3) {
+        NKP = (NK + 1) >> 1;
+    }
+};
+
+__device__ __forceinline__ void frag_split4(const float (&a)[4], uint32_t (&hi)[4], uint32_t (&lo)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split_tf32(a[i], hi[i], lo[i]);
+}
+__device__ __forceinline__ void frag_split2(const float (&b)[2], uint32_t (&hi)[2], uint32_t (&lo)[2]) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) split_tf32(b[i], hi[i], lo[i]);
+}
+
+// acc[nt] (+)= A[16 x 64] * B_nt[64 x 8]  for nt < NK:  A = 16 rows (clamped to the sample) of a row-major buffer (columns
+// [acol, acol + 64)), B_nt(k, n) = brows[r0 + nt * 8 + n][bcol + k].  Used for the logits (q . k') and for dp (do . v').
+template <int NKMAX>
+__device__ __forceinline__ void rows_dot_rows(float (&acc)[NKMAX][4], const float* abuf, int lda, int acol, const float* bbuf, int ldb, int bcol,
+                                              int r0, int m0, int N, int NK, int n0 = 0) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const float* pa0 = abuf + (r0 + min(m0 + g, N - 1)) * lda + acol + t;
+    const float* pa1 = abuf + (r0 + min(m0 + g + 8, N - 1)) * lda + acol + t;
+    const float* pb[NKMAX];
+#pragma unroll
+    for (int nt = 0; nt < NKMAX; ++nt) pb[nt] = bbuf + (r0 + min(n0 + nt * 8 + g, N - 1)) * ldb + bcol + t;
+#pragma unroll
+    for (int nt = 0; nt < NKMAX; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll 4
+    for (int kk = 0; kk < 8; ++kk) {
+        const float a[4] = {pa0[kk * 8], pa1[kk * 8], pa0[kk * 8 + 4], pa1[kk * 8 + 4]};
+        uint32_t ah[4], al[4];
+        frag_split4(a, ah, al);
+        // two key tiles at a time: their six HMMAs alternate between two accumulators
+#pragma unroll
+        for (int nt = 0; nt < NKMAX; nt += 2)
+            if (nt < NK) {
+                const bool two = (nt + 1 < NKMAX) && (nt + 1 < NK);
+                uint32_t bh0[2], bl0[2], bh1[2], bl1[2];
+                const float b0[2] = {pb[nt][kk * 8], pb[nt][kk * 8 + 4]};
+                frag_split2(b0, bh0, bl0);
+                if (nt + 1 < NKMAX) {
+                    const float b1[2] = {pb[nt + 1 < NKMAX ? nt + 1 : nt][kk * 8], pb[nt + 1 < NKMAX ? nt + 1 : nt][kk * 8 + 4]};
+                    frag_split2(b1, bh1, bl1);
+                }
+                hmma_tf32(acc[nt], al, bh0);
+                if (nt + 1 < NKMAX) { if (two) hmma_tf32(acc[nt + 1 < NKMAX ? nt + 1 : nt], al, bh1); }
+                hmma_tf32(acc[nt], ah, bl0);
+                if (nt + 1 < NKMAX) { if (two) hmma_tf32(acc[nt + 1 < NKMAX ? nt + 1 : nt], ah, bl1); }
+                hmma_tf32(acc[nt], ah, bh0);
+                if (nt + 1 < NKMAX) { if (two) hmma_tf32(acc[nt + 1 < NKMAX ? nt + 1 : nt], ah, bh1); }
+            }
     }
 }
 
-// Geometry of the block-diagonal tiling of one pass (S_act samples of N beads).
-struct AttnGeo {
-    int N, NP, S_act, MB, NK;       // beads, beads padded to 4, samples, 16-row blocks per sample, 8-key blocks per sample
-    __device__ __forceinline__ AttnGeo(int N_, int NP_, int S_) : N(N_), NP(NP_), S_act(S_), MB((N_ + 15) >> 4), NK((N_ + 7) >> 3) {}
-};
-
-// fragment loaders -----------------------------------------------------------------------------------------------
-// A operand = 16 rows [rbase + m0 .. + 15] (clamped to the sample) of a row-major buffer, k = column
-struct LoadA_rows {
-    const float* p0; const float* p1;          // rows g and g + 8 (already clamped), at column t
-    __device__ __forceinline__ LoadA_rows(const float* buf, int ld, int r0, int m0, int N, int coloff) {
-        const int g = (threadIdx.x & 31) >> 2, t = threadIdx.x & 3;
-        p0 = buf + (r0 + min(m0 + g, N - 1)) * ld + coloff + t;
-        p1 = buf + (r0 + min(m0 + g + 8, N - 1)) * ld + coloff + t;
-    }
-    __device__ __forceinline__ void operator()(int kk, float (&a)[4]) const {
-        a[0] = p0[kk * 8]; a[1] = p1[kk * 8]; a[2] = p0[kk * 8 + 4]; a[3] = p1[kk * 8 + 4];
-    }
-};
-// A operand = 16 rows of a [row][key] weight buffer (p or ds), k = key index masked to the sample's N keys
-struct LoadA_keys {
-    const float* p0; const float* p1; int N, t;
-    __device__ __forceinline__ LoadA_keys(const float* buf, int NP, int r0, int m0, int N_) : N(N_) {
-        const int g = (threadIdx.x & 31) >> 2;
-        t = threadIdx.x & 3;
-        p0 = buf + (r0 + min(m0 + g, N - 1)) * NP;
-        p1 = buf + (r0 + min(m0 + g + 8, N - 1)) * NP;
-    }
-    __device__ __forceinline__ void operator()(int kk, float (&a)[4]) const {
+// One 16 x 16 output block (two 8-column tiles dt, dt + 1) of  W[16 x keys] * B[keys x 64]:
+//   TRANSPOSED = false:  A(m, k) = wbuf[r0 + m0 + m][k]        (p or ds rows, k = key)                -> P V', dS K'
+//   TRANSPOSED = true :  A(m, k) = wbuf[r0 + k][m0 + m]        (m = key, k = query)                   -> dS^T Q, P^T dO
+//   B(k, n) = bbuf[r0 + k][bcol + dt * 8 + n]
+template <bool TRANSPOSED>
+__device__ __forceinline__ void keys_dot_cols(float (&acc)[2][4], const float* wbuf, int NP, const float* bbuf, int ldb, int bcol,
+                                              int r0, int m0, int N, int NK, int dt) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int ma = min(m0 + g, N - 1), mb = min(m0 + g + 8, N - 1);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+    const float* wb = wbuf + r0 * NP;
+    const float* bb = bbuf + r0 * ldb + bcol + dt * 8 + g;
+    for (int kk = 0; kk < NK; ++kk) {
         const int k0 = kk * 8 + t, k1 = k0 + 4;
         const bool v0 = k0 < N, v1 = k1 < N;
-        a[0] = v0 ? p0[k0] : 0.f; a[1] = v0 ? p1[k0] : 0.f; a[2] = v1 ? p0[k1] : 0.f; a[3] = v1 ? p1[k1] : 0.f;
+        const int c0 = min(k0, N - 1), c1 = min(k1, N - 1);
+        float a[4];
+        if (TRANSPOSED) {
+            a[0] = v0 ? wb[c0 * NP + ma] : 0.f; a[1] = v0 ? wb[c0 * NP + mb] : 0.f;
+            a[2] = v1 ? wb[c1 * NP + ma] : 0.f; a[3] = v1 ? wb[c1 * NP + mb] : 0.f;
+        } else {
+            a[0] = v0 ? wb[ma * NP + c0] : 0.f; a[1] = v0 ? wb[mb * NP + c0] : 0.f;
+            a[2] = v1 ? wb[ma * NP + c1] : 0.f; a[3] = v1 ? wb[mb * NP + c1] : 0.f;
+        }
+        uint32_t ah[4], al[4];
+        frag_split4(a, ah, al);
+        uint32_t bh[2][2], bl[2][2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const float b[2] = {bb[c0 * ldb + j * 8], bb[c1 * ldb + j * 8]};
+            frag_split2(b, bh[j], bl[j]);
+        }
+        hmma_tf32(acc[0], al, bh[0]); hmma_tf32(acc[1], al, bh[1]);
+        hmma_tf32(acc[0], ah, bl[0]); hmma_tf32(acc[1], ah, bl[1]);
+        hmma_tf32(acc[0], ah, bh[0]); hmma_tf32(acc[1], ah, bh[1]);
     }
-};
-// A operand = TRANSPOSE of a [row i][key j] weight buffer: m = key j0 + .., k = query i (masked to N)
-struct LoadA_keysT {
-    const float* base; int NP, N, j0, j1, t;
-    __device__ __forceinline__ LoadA_keysT(const float* buf, int NP_, int r0, int m0, int N_) : NP(NP_), N(N_) {
-        const int g = (threadIdx.x & 31) >> 2;
-        t = threadIdx.x & 3;
-        base = buf + r0 * NP;
-        j0 = min(m0 + g, N - 1); j1 = min(m0 + g + 8, N - 1);
+}
+
+// 16 x 8 tile  rows[16 x 64] * edge[64 x 4]:  u = A_h^T q  or  w = A_h^T do  (columns 0..2; column 3 is zero)
+__device__ __forceinline__ void rows_dot_edge(float (&acc)[4], const float* abuf, int lda, const float* __restrict__ Aedge, int hc, int r0, int m0, int N) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const float* pa0 = abuf + (r0 + min(m0 + g, N - 1)) * lda + t;
+    const float* pa1 = abuf + (r0 + min(m0 + g + 8, N - 1)) * lda + t;
+    const bool on = g < 3;
+    const float* pe = Aedge + (hc * 64 + t) * 4 + (on ? g : 0);
+    float e[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) e[i] = on ? __ldg(pe + i * 16) : 0.f;       // all 16 loads in flight at once
+    acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+    float c1[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+        const float a[4] = {pa0[kk * 8], pa1[kk * 8], pa0[kk * 8 + 4], pa1[kk * 8 + 4]};
+        const float b[2] = {e[2 * kk], e[2 * kk + 1]};
+        uint32_t ah[4], al[4], bh[2], bl[2];
+        frag_split4(a, ah, al);
+        frag_split2(b, bh, bl);
+        hmma_tf32(c1, al, bh); hmma_tf32(c2, ah, bl); hmma_tf32(acc, ah, bh);
     }
-    __device__ __forceinline__ void operator()(int kk, float (&a)[4]) const {
-        const int i0 = kk * 8 + t, i1 = i0 + 4;
-        const bool v0 = i0 < N, v1 = i1 < N;
-        const float* r0p = base + min(i0, N - 1) * NP;
-        const float* r1p = base + min(i1, N - 1) * NP;
-        a[0] = v0 ? r0p[j0] : 0.f; a[1] = v0 ? r0p[j1] : 0.f; a[2] = v1 ? r1p[j0] : 0.f; a[3] = v1 ? r1p[j1] : 0.f;
-    }
-};
-// B operand, n = row of a row-major buffer (a key), k = column:  B(k, n) = buf[r0 + n0 + n][coloff + k]
-struct LoadB_rowsN {
-    const float* p;
-    __device__ __forceinline__ LoadB_rowsN(const float* buf, int ld, int r0, int n0, int N, int coloff) {
-        const int g = (threadIdx.x & 31) >> 2, t = threadIdx.x & 3;
-        p = buf + (r0 + min(n0 + g, N - 1)) * ld + coloff + t;
-    }
-    __device__ __forceinline__ void operator()(int kk, float (&b)[2]) const { b[0] = p[kk * 8]; b[1] = p[kk * 8 + 4]; }
-};
-// B operand, k = row of a row-major buffer (a key / query; rows beyond the sample are clamped, their A entries are zero),
-// n = column:  B(k, n) = buf[r0 + k][coloff + n0 + n]
-struct LoadB_rowsK {
-    const float* base; int ld, N, t;
-    __device__ __forceinline__ LoadB_rowsK(const float* buf, int ld_, int r0, int n0, int N_, int coloff) : ld(ld_), N(N_) {
-        const int g = (threadIdx.x & 31) >> 2;
-        t = threadIdx.x & 3;
-        base = buf + r0 * ld + coloff + n0 + g;
-    }
-    __device__ __forceinline__ void operator()(int kk, float (&b)[2]) const {
-        b[0] = base[min(kk * 8 + t, N - 1) * ld];
-        b[1] = base[min(kk * 8 + t + 4, N - 1) * ld];
-    }
-};
-// B operand = folded edge map of the head: B(k = d, n = c) = A[hc * 64 + d][c] for c < 3 (rows of W.A are (a0, a1, a2, 0))
-struct LoadB_edge {
-    const float* p; bool on;
-    __device__ __forceinline__ LoadB_edge(const float* __restrict__ A, int hc) {
-        const int g = (threadIdx.x & 31) >> 2, t = threadIdx.x & 3;
-        on = g < 3;
-        p = A + (hc * 64 + t) * 4 + (on ? g : 0);
-    }
-    __device__ __forceinline__ void operator()(int kk, float (&b)[2]) const {
-        b[0] = on ? __ldg(p + kk * 32) : 0.f;
-        b[1] = on ? __ldg(p + kk * 32 + 16) : 0.f;
-    }
-};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i] += c1[i] + c2[i];
+}
 
 // ---------------------------------------------------------------------------------------------------------------
-// Forward phase 1: logits  sP[u][j] = s q_u . k'_j   (tiles: sample x row block x key block)
+// Forward phase 1: scaled logits  sP[u][j] = s q_u . k'_j   (items: sample x row block x key-tile pair)
 template <class C>
-__device__ __forceinline__ void attn_logits_mma(const float* sQKV, float* sP, const AttnGeo& G) {
+__device__ __forceinline__ void attn_logits_items(const float* sQKV, float* sP, const AttnGeo& G) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    const int per = G.MB * G.NK, items = G.S_act * per;
+    const int per = G.MB * G.NKP, items = G.S_act * per;
     for (int it = warp; it < items; it += kCW) {
-        const int s = it / per, rem = it - s * per, mb = rem / G.NK, nt = rem - mb * G.NK;
-        const int r0 = s * G.N;
-        float c[4] = {0.f, 0.f, 0.f, 0.f};
-        tile_mma(c, 8, LoadA_rows(sQKV, C::LDQ, r0, mb * 16, G.N, 0), LoadB_rowsN(sQKV, C::LDQ, r0, nt * 8, G.N, 64));
-        const int col = nt * 8 + 2 * t;
-        if (col < G.NP) {
-            const int ra = mb * 16 + g, rb = ra + 8;
-            if (ra < G.N) *reinterpret_cast<float2*>(sP + (r0 + ra) * G.NP + col) = make_float2(kAttnScale * c[0], kAttnScale * c[1]);
-            if (rb < G.N) *reinterpret_cast<float2*>(sP + (r0 + rb) * G.NP + col) = make_float2(kAttnScale * c[2], kAttnScale * c[3]);
+        const int s = it / per, rem = it - s * per, mb = rem / G.NKP, np = rem - mb * G.NKP;
+        const int r0 = s * G.N, m0 = mb * 16, n0 = np * 16;
+        float c[2][4];
+        rows_dot_rows<2>(c, sQKV, C::LDQ, 0, sQKV, C::LDQ, 64, r0, m0, G.N, min(2, G.NK - 2 * np), n0);
+        const int ra = m0 + g, rb = ra + 8;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int col = n0 + j * 8 + 2 * t;
+            if (col < G.NP) {
+                if (ra < G.N) *reinterpret_cast<float2*>(sP + (r0 + ra) * G.NP + col) = make_float2(kAttnScale * c[j][0], kAttnScale * c[j][1]);
+                if (rb < G.N) *reinterpret_cast<float2*>(sP + (r0 + rb) * G.NP + col) = make_float2(kAttnScale * c[j][2], kAttnScale * c[j][3]);
+            }
         }
     }
 }
@@ -173,54 +227,64 @@ __device__ __forceinline__ void attn_softmax_rows(float* sP, float* st_p, const 
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
         const float e0 = a0 ? expf(l0 - m) : 0.f, e1 = a1 ? expf(l1 - m) : 0.f;
-        const float sum = warp_sum(e0 + e1);
-        const float p0 = e0 / sum, p1 = e1 / sum;
+        const float inv = 1.0f / warp_sum(e0 + e1);
+        const float p0 = e0 * inv, p1 = e1 * inv;
         if (lane < G.NP) { row[lane] = p0; st_p[(size_t)r * G.NP + lane] = p0; }
         if (lane + 32 < G.NP) { row[lane + 32] = p1; st_p[(size_t)r * G.NP + lane + 32] = p1; }
     }
 }
-// Forward phase 3: o_u = sum_j p_uj v'_j - A x_u + c  -> canonical hi/lo operand of the out-projection (the rotating slot).
-// f_store(row, col, v0, v1) receives two consecutive columns (col even) of an active row.
+// Forward phase 3 / reverse dq phase: 16 x 16 blocks of  W[rows x keys] * B[keys x 64]  -> f_store(row, col, v0, v1)
+// (items: sample x row block x column-tile pair; 4 pairs cover the 64 columns)
 template <class C, class F>
-__device__ __forceinline__ void attn_weighted_mma(const float* sW, const float* sB, int ldb, int coloff, const AttnGeo& G, F f_store) {
+__device__ __forceinline__ void attn_weighted_items(const float* sW, const float* sB, int ldb, int bcol, const AttnGeo& G, F f_store) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    const int per = G.MB * 8, items = G.S_act * per;
+    const int per = G.MB * 4, items = G.S_act * per;
     for (int it = warp; it < items; it += kCW) {
-        const int s = it / per, rem = it - s * per, mb = rem >> 3, nt = rem & 7;
-        const int r0 = s * G.N;
-        float c[4] = {0.f, 0.f, 0.f, 0.f};
-        tile_mma(c, G.NK, LoadA_keys(sW, G.NP, r0, mb * 16, G.N), LoadB_rowsK(sB, ldb, r0, nt * 8, G.N, coloff));
-        const int ra = mb * 16 + g, rb = ra + 8, col = nt * 8 + 2 * t;
-        if (ra < G.N) f_store(r0 + ra, col, c[0], c[1]);
-        if (rb < G.N) f_store(r0 + rb, col, c[2], c[3]);
+        const int s = it / per, rem = it - s * per, mb = rem >> 2, dp = rem & 3;
+        const int r0 = s * G.N, m0 = mb * 16;
+        float c[2][4];
+        keys_dot_cols<false>(c, sW, G.NP, sB, ldb, bcol, r0, m0, G.N, G.NK, 2 * dp);
+        const int ra = m0 + g, rb = ra + 8;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int col = (2 * dp + j) * 8 + 2 * t;
+            if (ra < G.N) f_store(r0 + ra, col, c[j][0], c[j][1]);
+            if (rb < G.N) f_store(r0 + rb, col, c[j][2], c[j][3]);
+        }
     }
 }
 
 // Reverse phase 1: dp_uj = do_u . v'_j -> sDS (raw);  u_u = A_h^T q_u -> sQKV[u][192..194];  w_u = A_h^T do_u -> sO[u][64..66]
 template <class C>
-__device__ __forceinline__ void attn_dp_uw_mma(float* sQKV, float* sO, float* sDS, const float* __restrict__ Aedge, int hc, const AttnGeo& G) {
+__device__ __forceinline__ void attn_dp_uw_items(float* sQKV, float* sO, float* sDS, const float* __restrict__ Aedge, int hc, const AttnGeo& G) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    const int per = G.MB * (G.NK + 2), items = G.S_act * per;
+    const int per = G.MB * (G.NKP + 2), items = G.S_act * per;
+    // the u / w items go first in the deal (to the low warps), the dp items follow: with <= 16 items every warp has one
     for (int it = warp; it < items; it += kCW) {
-        const int s = it / per, rem = it - s * per, mb = rem / (G.NK + 2), nt = rem - mb * (G.NK + 2);
-        const int r0 = s * G.N;
-        const int ra = mb * 16 + g, rb = ra + 8;
-        float c[4] = {0.f, 0.f, 0.f, 0.f};
-        if (nt < G.NK) {
-            tile_mma(c, 8, LoadA_rows(sO, C::LDO, r0, mb * 16, G.N, 0), LoadB_rowsN(sQKV, C::LDQ, r0, nt * 8, G.N, 128));
-            const int col = nt * 8 + 2 * t;
-            if (col < G.NP) {
-                if (ra < G.N) *reinterpret_cast<float2*>(sDS + (r0 + ra) * G.NP + col) = make_float2(c[0], c[1]);
-                if (rb < G.N) *reinterpret_cast<float2*>(sDS + (r0 + rb) * G.NP + col) = make_float2(c[2], c[3]);
+        const int s = it / per, rem = it - s * per, mb = rem / (G.NKP + 2), np = rem - mb * (G.NKP + 2);
+        const int r0 = s * G.N, m0 = mb * 16;
+        const int ra = m0 + g, rb = ra + 8;
+        if (np < G.NKP) {
+            const int n0 = np * 16;
+            float c[2][4];
+            rows_dot_rows<2>(c, sO, C::LDO, 0, sQKV, C::LDQ, 128, r0, m0, G.N, min(2, G.NK - 2 * np), n0);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int col = n0 + j * 8 + 2 * t;
+                if (col < G.NP) {
+                    if (ra < G.N) *reinterpret_cast<float2*>(sDS + (r0 + ra) * G.NP + col) = make_float2(c[j][0], c[j][1]);
+                    if (rb < G.N) *reinterpret_cast<float2*>(sDS + (r0 + rb) * G.NP + col) = make_float2(c[j][2], c[j][3]);
+                }
             }
         } else {
-            const bool is_u = nt == G.NK;
+            const bool is_u = np == G.NKP;
             float* dst = is_u ? sQKV : sO;
             const int ld = is_u ? C::LDQ : C::LDO, off = is_u ? 192 : 64;
-            tile_mma(c, 8, LoadA_rows(dst, ld, r0, mb * 16, G.N, 0), LoadB_edge(Aedge, hc));
+            float e4[4];
+            rows_dot_edge(e4, dst, ld, Aedge, hc, r0, m0, G.N);
             if (t < 2) {        // columns 2t, 2t + 1 of the 8-wide tile: (0, 1) and (2, 3); column 3 is zero
-                if (ra < G.N) *reinterpret_cast<float2*>(dst + (r0 + ra) * ld + off + 2 * t) = make_float2(c[0], c[1]);
-                if (rb < G.N) *reinterpret_cast<float2*>(dst + (r0 + rb) * ld + off + 2 * t) = make_float2(c[2], c[3]);
+                if (ra < G.N) *reinterpret_cast<float2*>(dst + (r0 + ra) * ld + off + 2 * t) = make_float2(e4[0], e4[1]);
+                if (rb < G.N) *reinterpret_cast<float2*>(dst + (r0 + rb) * ld + off + 2 * t) = make_float2(e4[2], e4[3]);
             }
         }
     }
@@ -240,55 +304,63 @@ __device__ __forceinline__ void attn_ds_rows(const float* sP, float* sDS, const 
         if (lane + 32 < G.NP) dr[lane + 32] = p1 * (d1 - tsum);
     }
 }
-// Reverse phase 3: dx_j += sum_i (p_ij w_i + s ds_ij u_i) - w_j.  One thread per (key row, component): deterministic.
+// Reverse phase 3: dx_j += sum_i (p_ij w_i + s ds_ij u_i) - w_j.  Four lanes per (key row, component), fixed summation order: deterministic.
 template <class C>
 __device__ __forceinline__ void attn_dx_rows(const float* sQKV, const float* sO, const float* sP, const float* sDS, float* sDX, const AttnGeo& G) {
     const int rows = G.S_act * G.N;
-    for (int idx = threadIdx.x; idx < rows * 3; idx += kCT) {
+    const int q = threadIdx.x & 3;
+    for (int base = 0; base < rows * 3; base += kCT / 4) {         // warp-uniform trip count (the quad shuffles need whole warps)
+        const int idx0 = base + (threadIdx.x >> 2);
+        const bool valid = idx0 < rows * 3;
+        const int idx = valid ? idx0 : 0;
         const int j = idx / 3, cc = idx - j * 3;
         const int r0 = (j / G.N) * G.N, jj = j - r0;
         float acc = 0.f, acd = 0.f;
-        for (int i = 0; i < G.N; ++i) {
+        for (int i = q; i < G.N; i += 4) {
             acc = fmaf(sP[(r0 + i) * G.NP + jj], sO[(r0 + i) * C::LDO + 64 + cc], acc);
             acd = fmaf(sDS[(r0 + i) * G.NP + jj], sQKV[(r0 + i) * C::LDQ + 192 + cc], acd);
         }
-        sDX[j * 4 + cc] += (acc + kAttnScale * acd) - sO[j * C::LDO + 64 + cc];
+        float v = acc + kAttnScale * acd;
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        if (valid && q == 0) sDX[j * 4 + cc] += v - sO[j * C::LDO + 64 + cc];
     }
 }
-// Reverse phases 4-6: 16 x 8 tiles of  dq = s dS K'  (TRANSPOSED = false, weights sDS, B = k' columns) or
-// dk' = s dS^T Q / dv' = P^T dO (TRANSPOSED = true) into registers (up to MAXT tiles per warp and round), then into the
-// rotating slot once the tensor core has released it -- the MMAs of the previous slot job overlap the tile arithmetic.
-template <class C, bool TRANSPOSED, class CTX>
-__device__ __forceinline__ void attn_grad_to_slot_mma(CTX& c, const float* sW, const float* sB, int ldb, int coloff, float scale, const AttnGeo& G) {
-    constexpr int MAXT = 4;
+// Reverse phases 4-5: 16 x 16 blocks of  dk' = s dS^T Q  (wbuf = sDS, bbuf = q columns)  or  dv' = P^T dO  (wbuf = sP, bbuf = sO)
+// into registers (two items per warp and round), then into the rotating slot once the tensor core has released it -- the MMAs
+// of the previous slot job overlap the arithmetic.
+template <class C, class CTX>
+__device__ __forceinline__ void attn_keys_to_slot_items(CTX& c, const float* wbuf, const float* bbuf, int ldb, float scale, const AttnGeo& G) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    const int per = G.MB * 8, items = G.S_act * per;
-    for (int base = warp; base < items; base += kCW * MAXT) {
-        float acc[MAXT][4];
-#pragma unroll
-        for (int q = 0; q < MAXT; ++q) {
-            acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.f;
-            const int it = base + q * kCW;
-            if (it < items) {
-                const int s = it / per, rem = it - s * per, mb = rem >> 3, nt = rem & 7;
-                const int r0 = s * G.N;
-                if (TRANSPOSED) tile_mma(acc[q], G.NK, LoadA_keysT(sW, G.NP, r0, mb * 16, G.N), LoadB_rowsK(sB, ldb, r0, nt * 8, G.N, coloff));
-                else tile_mma(acc[q], G.NK, LoadA_keys(sW, G.NP, r0, mb * 16, G.N), LoadB_rowsK(sB, ldb, r0, nt * 8, G.N, coloff));
-            }
+    const int per = G.MB * 4, items = G.S_act * per;
+    for (int base = warp; base < items; base += 2 * kCW) {
+        float a0[2][4], a1[2][4];
+        const int it1 = base + kCW;
+        {
+            const int s = base / per, rem = base - s * per;
+            keys_dot_cols<true>(a0, wbuf, G.NP, bbuf, ldb, 0, s * G.N, (rem >> 2) * 16, G.N, G.NK, 2 * (rem & 3));
+        }
+        if (it1 < items) {
+            const int s = it1 / per, rem = it1 - s * per;
+            keys_dot_cols<true>(a1, wbuf, G.NP, bbuf, ldb, 0, s * G.N, (rem >> 2) * 16, G.N, G.NK, 2 * (rem & 3));
         }
         c.slot_acquire();
 #pragma unroll
-        for (int q = 0; q < MAXT; ++q) {
-            const int it = base + q * kCW;
+        for (int h = 0; h < 2; ++h) {
+            const int it = base + h * kCW;
             if (it < items) {
-                const int s = it / per, rem = it - s * per, mb = rem >> 3, nt = rem & 7;
-                const int r0 = s * G.N, ra = mb * 16 + g, rb = ra + 8, col = nt * 8 + 2 * t;
-                if (ra < G.N) can_store2<C::kCS>(c.slot_hi, c.slot_lo, r0 + ra, col, scale * acc[q][0], scale * acc[q][1]);
-                if (rb < G.N) can_store2<C::kCS>(c.slot_hi, c.slot_lo, r0 + rb, col, scale * acc[q][2], scale * acc[q][3]);
+                const int s = it / per, rem = it - s * per, r0 = s * G.N, m0 = (rem >> 2) * 16, dp = rem & 3;
+                const int ra = m0 + g, rb = ra + 8;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int col = (2 * dp + j) * 8 + 2 * t;
+                    const float (&a)[2][4] = h ? a1 : a0;
+                    if (ra < G.N) can_store2<C::kCS>(c.slot_hi, c.slot_lo, r0 + ra, col, scale * a[j][0], scale * a[j][1]);
+                    if (rb < G.N) can_store2<C::kCS>(c.slot_hi, c.slot_lo, r0 + rb, col, scale * a[j][2], scale * a[j][3]);
+                }
             }
         }
     }
-    c.slot_acquire();       // warps without a tile still take part in the hand-off bookkeeping
 }
 
 }  // namespace v2

@@ -10,11 +10,13 @@
 #include <string>
 #include <vector>
 
+#define DFF_HOST_TU 1
 #include "../../include/dff_b200.h"
 #include "dff_kernel.cuh"
 #include "dff_tc.cuh"
 #include "dff_kernel_tc.cuh"
 #include "dff_metrics.cuh"
+#include "dff_tc_configs.h"
 
 using namespace dff;
 
@@ -67,7 +69,8 @@ struct dff_model {
     size_t d_io_cap[6] = {0, 0, 0, 0, 0, 0};
     uint32_t* d_flags = nullptr;
     float* d_sched = nullptr;  size_t d_sched_T = 0;
-    int last_R = 0, last_S = 0;
+    int last_R = 0, last_S = 0, last_att = 0;
+    bool attn_mma = false;          // default attention flavour of the tcgen05 kernel for this model (set at create)
     const char* last_cfg = "none";
     // tcgen05 configuration (hidden = 64): job table + canonical hi/lo weight panels
     bool tc_ok = false;
@@ -103,32 +106,40 @@ struct Packer {
     }
 };
 
-template <class C, int MINB>
-int launch_cfg(dff_model* m, const ModelDev& M, const StepArgs& A, int grid, cudaStream_t stream) {
-    static bool attr_set[8] = {false};
-    auto kern = dff_fused_kernel<C, MINB>;
-    const size_t smem = C::kSmemBytes;
-    if (!attr_set[m->device & 7]) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[m->device & 7] = true;
-    }
-    kern<<<grid, kThreads, smem, stream>>>(M, A);
-    CUDA_TRY(cudaGetLastError());
+// kernels live in their own translation units (dff_tc_inst.cu, dff_legacy_inst.cu), one configuration each
+#define DFF_TC_DECL(PN, HP, R, ATT) \
+    extern "C" cudaError_t dff_tc_launch_##PN##_##HP##_##R##_##ATT(const ModelDev*, const StepArgs*, const v2::TcArgs*, int, cudaStream_t);
+DFF_TC_CONFIGS(DFF_TC_DECL)
+#undef DFF_TC_DECL
+extern "C" cudaError_t dff_legacy_launch_64_0(const ModelDev*, const StepArgs*, int, cudaStream_t);
+extern "C" cudaError_t dff_legacy_launch_64_1(const ModelDev*, const StepArgs*, int, cudaStream_t);
+extern "C" cudaError_t dff_legacy_launch_64_2(const ModelDev*, const StepArgs*, int, cudaStream_t);
+extern "C" cudaError_t dff_legacy_launch_128_0(const ModelDev*, const StepArgs*, int, cudaStream_t);
+extern "C" cudaError_t dff_legacy_launch_128_1(const ModelDev*, const StepArgs*, int, cudaStream_t);
+extern "C" cudaError_t dff_legacy_launch_128_2(const ModelDev*, const StepArgs*, int, cudaStream_t);
+
+using TcLaunchFn = cudaError_t (*)(const ModelDev*, const StepArgs*, const v2::TcArgs*, int, cudaStream_t);
+using LegacyLaunchFn = cudaError_t (*)(const ModelDev*, const StepArgs*, int, cudaStream_t);
+
+TcLaunchFn tc_launcher(int PN, int HP, int R, int ATT) {
+#define DFF_TC_PICK(pn, hp, r, att) if (PN == pn && HP == hp && R == r && ATT == att) return dff_tc_launch_##pn##_##hp##_##r##_##att;
+    DFF_TC_CONFIGS(DFF_TC_PICK)
+#undef DFF_TC_PICK
+    return nullptr;
+}
+
+int launch_legacy(dff_model* m, LegacyLaunchFn fn, const ModelDev& M, const StepArgs& A, int grid, cudaStream_t stream) {
+    cudaError_t e = fn(&M, &A, grid, stream);
+    if (e != cudaSuccess) return fail(DFF_ECUDA, "legacy kernel launch failed: %s", cudaGetErrorString(e));
     m->launches += 1;
     return DFF_OK;
 }
 
-template <class C>
-int launch_tc(dff_model* m, const ModelDev& M, const StepArgs& A, int grid, cudaStream_t stream) {
-    static bool attr_set[8] = {false};
-    auto kern = v2::dff_fused_tc_kernel<C>;
-    const size_t smem = C::kSmemBytes;
-    if (!attr_set[m->device & 7]) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[m->device & 7] = true;
-    }
-    kern<<<grid, v2::kTcThreads, smem, stream>>>(M, A, m->tc);
-    CUDA_TRY(cudaGetLastError());
+int launch_tc(dff_model* m, int PN, int HP, int R, int ATT, const ModelDev& M, const StepArgs& A, int grid, cudaStream_t stream) {
+    TcLaunchFn fn = tc_launcher(PN, HP, R, ATT);
+    if (!fn) return fail(DFF_EINVAL, "internal: no kernel instantiation TcCfg<%d,%d,%d,%d>", PN, HP, R, ATT);
+    cudaError_t e = fn(&M, &A, &m->tc, grid, stream);
+    if (e != cudaSuccess) return fail(DFF_ECUDA, "tcgen05 kernel launch failed: %s", cudaGetErrorString(e));
 #ifdef DFF_TC_PROFILE
     if (m->tc.dbg) {     // developer build: print the per-CTA wait-cycle breakdown of this launch (synchronises)
         std::vector<long long> h((size_t)grid * 16 + 32);
@@ -138,11 +149,11 @@ int launch_tc(dff_model* m, const ModelDev& M, const StepArgs& A, int grid, cuda
         for (int b = 0; b < grid; ++b) for (int i = 0; i < 16; ++i) s[i] += (double)h[(size_t)b * 16 + i] / grid;
         fprintf(stderr, "[tc profile] grid %d steps %d: compute total %.0f cyc; waits dq %.0f acc %.0f d1 %.0f slot %.0f | issuer total %.0f: post %.0f drain %.0f weights %.0f | producer empty-wait %.0f\n",
                 grid, A.n_steps, s[7], s[0], s[1], s[2], s[3], s[12], s[9], s[10], s[11], s[8]);
-        static const char* names[23] = {"f.init+ln", "dq_wait", "f.qkv_epi", "f.attn", "f.slot_post", "acc_wait", "f.acc_epi", "f.gate+post", "d1_wait", "f.d1copy",
+        static const char* names[28] = {"f.init+ln", "dq_wait", "f.qkv_epi", "f.attn", "f.slot_post", "acc_wait", "f.acc_epi", "f.gate+post", "d1_wait", "f.d1copy",
                                         "f.gelu", "b.gate2+post", "b.d1copy", "b.gelu'", "b.accepi+gate1+post", "b.reload_issue", "b.do_epi", "b.ds", "b.dq+post",
-                                        "b.dk+post", "b.dv+post", "b.acc+lnbwd", "integrator"};
+                                        "b.dk+post", "b.dv+post", "b.acc+lnbwd", "integrator", "f.logits", "f.softmax", "b.dp_uw", "b.dx", "b.dk'"};
         fprintf(stderr, "[tc phases, CTA 0, cycles per step]");
-        for (int i = 0; i < 23; ++i) fprintf(stderr, " %s %.0f |", names[i], (double)h[(size_t)grid * 16 + i] / A.n_steps);
+        for (int i = 0; i < 28; ++i) fprintf(stderr, " %s %.0f |", names[i], (double)h[(size_t)grid * 16 + i] / A.n_steps);
         fprintf(stderr, "\n");
     }
 #endif
@@ -193,24 +204,26 @@ int launch(dff_model* m, StepArgs& A, cudaStream_t stream) {
         if (grid > m->scratch_ctas) return fail(DFF_EINVAL, "internal: grid %d exceeds scratch slots %d", grid, m->scratch_ctas);
         const double slices = (double)((A.B / grid + 1 + S - 1) / S) * (double)A.n_steps * (double)m->tc.nslice_all;   // passes of the fullest CTA
         if (slices >= 4.0e9) return fail(DFF_EINVAL, "n_steps %d too large for one launch; split the call (e.g. per save interval)", A.n_steps);
-        m->last_R = 64; m->last_S = S; m->last_cfg = "tc";
+        m->last_R = 64; m->last_S = S;
+        // attention flavour: HMMA tiles (general path: every edge mode, the large-N nets) or the CUDA-core routines (small intrinsic nets)
+        int att = m->attn_mma ? 1 : 0;
+        if (const char* e = getenv("DFF_ATTN")) att = !strcmp(e, "mma") ? 1 : (!strcmp(e, "simt") ? 0 : att);
+        m->last_cfg = att ? "tc" : "tc";
+        m->last_att = att;
+        int PN, R = 64;
         if (m->HP == 64) {
-            if (m->NP <= 12) {
-                if (S * N <= 60) return launch_tc<v2::TcCfg<12, 64, 60>>(m, M, A, grid, stream);      // 4-stage ring
-                return launch_tc<v2::TcCfg<12, 64>>(m, M, A, grid, stream);
-            }
-            if (m->NP <= 32) return launch_tc<v2::TcCfg<32, 64>>(m, M, A, grid, stream);
-            return launch_tc<v2::TcCfg<64, 64>>(m, M, A, grid, stream);
+            if (m->NP <= 12) { PN = 12; if (S * N <= 60) R = 60; }      // 60-row buffers leave room for a 4th weight stage
+            else if (m->NP <= 32) PN = 32;
+            else PN = 64;
+        } else {
+            // hidden 96 / 128: passes of <= 60 rows (three 20-bead samples, twelve 5-bead samples) use 60-row buffers, which
+            // leaves room for a 4th weight stage
+            if (m->NP <= 12) { PN = 12; if (S * N <= 60) R = 60; }
+            else if (m->NP <= 20 && S * N <= 60) { PN = 20; R = 60; }
+            else if (m->NP <= 32) PN = 32;
+            else { PN = 56; R = 56; }     // one 33..56-bead sample per pass: 56-row buffers, 4-stage ring
         }
-        // hidden 96 / 128: passes of <= 60 rows (three 20-bead samples, twelve 5-bead samples) use 60-row buffers, which
-        // leaves room for a 4th weight stage
-        if (m->NP <= 12) {
-            if (S * N <= 60) return launch_tc<v2::TcCfg<12, 128, 60>>(m, M, A, grid, stream);
-            return launch_tc<v2::TcCfg<12, 128>>(m, M, A, grid, stream);
-        }
-        if (m->NP <= 20 && S * N <= 60) return launch_tc<v2::TcCfg<20, 128, 60>>(m, M, A, grid, stream);
-        if (m->NP <= 32) return launch_tc<v2::TcCfg<32, 128>>(m, M, A, grid, stream);
-        return launch_tc<v2::TcCfg<56, 128, 56>>(m, M, A, grid, stream);     // one 33..56-bead sample per pass: 56-row buffers, 4-stage ring
+        return launch_tc(m, PN, m->HP, R, att, M, A, grid, stream);
     }
     int R, S, ctas;
     ModelDev M;
@@ -230,14 +243,10 @@ int launch(dff_model* m, StepArgs& A, cudaStream_t stream) {
         if (slices >= 4.0e9) return fail(DFF_EINVAL, "n_steps %d too large for one launch; split the call (e.g. per save interval)", A.n_steps);
     }
     m->last_R = R; m->last_S = S; m->last_cfg = cfg == WIDE ? "wide" : cfg == TALL ? "tall" : "duo";
-    if (m->HP == 64) {
-        if (cfg == WIDE) return launch_cfg<Cfg<64, 64, 1>, 1>(m, M, A, grid, stream);
-        if (cfg == TALL) return launch_cfg<Cfg<64, 32, 2>, 1>(m, M, A, grid, stream);
-        return launch_cfg<Cfg<64, 32, 1, 2, 32>, (kThreads == 256 ? 2 : 1)>(m, M, A, grid, stream);
-    }
-    if (cfg == WIDE) return launch_cfg<Cfg<128, 64, 1>, 1>(m, M, A, grid, stream);
-    if (cfg == TALL) return launch_cfg<Cfg<128, 32, 2>, 1>(m, M, A, grid, stream);
-    return launch_cfg<Cfg<128, 32, 1, 2, 32>, (kThreads == 256 ? 2 : 1)>(m, M, A, grid, stream);
+    const int li = cfg == WIDE ? 0 : cfg == TALL ? 1 : 2;
+    static const LegacyLaunchFn legacy_fn[2][3] = {{dff_legacy_launch_64_0, dff_legacy_launch_64_1, dff_legacy_launch_64_2},
+                                                   {dff_legacy_launch_128_0, dff_legacy_launch_128_1, dff_legacy_launch_128_2}};
+    return launch_legacy(m, legacy_fn[m->HP == 64 ? 0 : 1][li], M, A, grid, stream);
 }
 
 int ensure_io(dff_model* m, int slot, size_t floats) {
@@ -445,6 +454,9 @@ int dff_model_create_ex(dff_model_t** out, int device, int num_beads, int hidden
         const int cD = HP, cA = (int)kColAcc;          // TMEM work area starts after the HP-column block accumulator
         const int cFF = cD + 256, cOut = HP == 64 ? cD + 384 : -1, cDn = HP == 64 ? cD + 128 + 2 * HP : -1;   // == TcCfg::kCorrFF / kCorrOut / kCorrDn
         const int nch64 = 4 * H / 64;                  // FF hidden chunks of 64 columns; "supers" of <= 4 chunks share the work area
+        // a 256-column super is issued as 192 + 64 column jobs when the stage holds 12 KB: both fill their weight slices completely
+        // ([hi | lo] of 8 x 192 and 24 x 64 floats), 128 + 128 would leave a third of every stage (and of the bytes in flight) unused
+        const int ff_split = (getenv("DFF_FF_SPLIT") ? atoi(getenv("DFF_FF_SPLIT")) : (HP == 64 ? 128 : 192));
         for (int l = 0; l < L; ++l) {
             const float *Wq = LW(l, 2), *bq = LW(l, 3), *Wkv = LW(l, 4), *bkv = LW(l, 5), *Wo = LW(l, 8), *W1 = LW(l, 13), *W2 = LW(l, 15);
             const size_t oA = lo[l].A;
@@ -470,10 +482,10 @@ int dff_model_create_ex(dff_model_t** out, int device, int num_beads, int hidden
             // for a post (LN2 output ready / work area drained), the last one commits d1_ready
             for (int c0 = 0; c0 < nch64; c0 += 4) {
                 const int w = std::min(4, nch64 - c0) * 64;
-                for (int q = 0; q < w; q += 128) {
-                    const int wq = std::min(128, w - q);
+                for (int q = 0; q < w; q += ff_split) {
+                    const int wq = std::min(ff_split, w - q);
                     job(H, wq, [&](int k, int j) -> float { return W1[(size_t)(c0 * 64 + q + j) * H + k]; }, cD + q,
-                        (q == 0 ? TCJ_WAIT_POST : 0) | (q + 128 >= w ? TCJ_COMMIT_D1 : 0));
+                        (q == 0 ? TCJ_WAIT_POST : 0) | (q + ff_split >= w ? TCJ_COMMIT_D1 : 0));
                 }
             }
             for (int c2 = 0; c2 < nch64; ++c2)
@@ -485,10 +497,10 @@ int dff_model_create_ex(dff_model_t** out, int device, int num_beads, int hidden
             const float *Wq = LW(l, 2), *Wkv = LW(l, 4), *Wo = LW(l, 8), *W1 = LW(l, 13), *W2 = LW(l, 15);
             for (int c0 = 0; c0 < nch64; c0 += 4) {
                 const int w = std::min(4, nch64 - c0) * 64;
-                for (int q = 0; q < w; q += 128) {
-                    const int wq = std::min(128, w - q);
+                for (int q = 0; q < w; q += ff_split) {
+                    const int wq = std::min(ff_split, w - q);
                     job(H, wq, [&](int d, int j) -> float { return W2[(size_t)d * 4 * H + c0 * 64 + q + j]; }, cD + q,
-                        (q == 0 ? TCJ_WAIT_POST : 0) | (q + 128 >= w ? TCJ_COMMIT_D1 : 0));
+                        (q == 0 ? TCJ_WAIT_POST : 0) | (q + ff_split >= w ? TCJ_COMMIT_D1 : 0));
                 }
             }
             for (int c2 = 0; c2 < nch64; ++c2)

@@ -43,6 +43,7 @@ constexpr int kComputeThreads = kCT;
 constexpr int kTcThreads = kComputeThreads + 64;   // + TMA producer warp + MMA issuer warp
 constexpr int kTcStages = 3;
 constexpr int kJobCap = 200;              // job-table entries (16 B each) cached in shared memory
+constexpr int B_COUNT_ = 26;              // uint64 slots of the barrier block (== B_COUNT below)
 
 // TMEM column map (fp32 columns, 64 lanes used): [0, HP) block accumulator (att / ff / d m_hat / d n_hat), then at HP the
 // work area: 2 x 192 q|k'|v' double buffer, <= 256 columns of FF hidden, 2 x 64 d o double buffer.   HP + 384 <= 512.
@@ -83,9 +84,12 @@ struct TcArgs {
 // HP = 64 (hidden 64) keeps the node stream in shared memory and uses 16 KB weight stages; HP = 128 (hidden 96 / 128) keeps
 // the node stream in the per-CTA global scratch (row passes only, coalesced, L2 resident) and uses 12 KB stages -- that is
 // what lets the fp32 hi/lo operands of a 64-row tile (8 bytes per element) fit 227 KB.
-template <int PN_, int HP_, int R_ = 64>
+// ATT_ selects how the attention contractions run: 0 = CUDA-core row / pair / quad routines (fastest for the small
+// intrinsic-coordinate nets: chignolin, ala2, trp-cage), 1 = warp-level tensor-core tiles (dff_attn_mma.cuh: the general path).
+template <int PN_, int HP_, int R_ = 64, int ATT_ = 0>
 struct TcCfg {
-    static constexpr int kHP = HP_, kR = R_, kHC = 1, kPN = PN_;      // kR node rows per pass (<= 64 = the MMA M; smaller frees shared memory)
+    static constexpr int kHP = HP_, kR = R_, kHC = 1, kPN = PN_;
+    static constexpr bool kAttMma = ATT_ != 0;      // kR node rows per pass (<= 64 = the MMA M; smaller frees shared memory)
     static constexpr int kCS = kR * 4 + 4;    // canonical chunk stride in floats (kR rows x 16 B + 16 B pad: bank spread)
     static constexpr int CWQ = 64, NCH = kHeads;
     static constexpr int LDH = kHP + 4;
@@ -123,7 +127,7 @@ struct TcCfg {
     static constexpr int oTmp = oDX + kR * 4;
     static constexpr int oJobs = oTmp + kR * 4;
     static constexpr int oBar = oJobs + kJobCap * 4;
-    static constexpr int kFloats = oBar + 32;
+    static constexpr int kFloats = oBar + 2 * B_COUNT_ + 4;
     static constexpr size_t kSmemBytes = (size_t)kFloats * sizeof(float);
     static_assert(kR * LDH <= kR * LDQ, "row buffer must fit the q|k'|v' buffer");
     static_assert(oNhatHi % 4 == 0 && oSlotHi % 4 == 0 && oW % 4 == 0 && oJobs % 4 == 0 && oBar % 4 == 0, "16-byte alignment");
@@ -131,26 +135,21 @@ struct TcCfg {
     static_assert(kColD + 384 <= kTmemCols && kColD + 128 + 2 * kHP <= kTmemCols, "TMEM column budget");
 };
 
-// barrier / counter block at oBar (uint64 slots)
-enum { B_FULL = 0, B_EMPTY = 4, B_DQ = 8, B_ACC = 10, B_D1 = 11, B_SLOT = 12, B_COUNT = 13 };      // room for 4 ring stages
+// barrier block at oBar (uint64 slots).  Every hand-off of the kernel is an mbarrier (round 1 polled two progress counters with
+// st.volatile / ld.acquire; the arrive / try_wait pair is the documented release / acquire pattern and costs the same).
+//   B_POST  ring of 8: compute -> issuer "operand ready" (post i arrives on slot i & 7; the compute warps can never be more than
+//           two posts ahead of the issuer: every slot_post first waits for the previous slot job)
+//   B_DRAIN 2: compute -> issuer "double-buffered accumulator b read back"
+enum { B_FULL = 0, B_EMPTY = 4, B_DQ = 8, B_ACC = 10, B_D1 = 11, B_SLOT = 12, B_POST = 16, B_DRAIN = 24, B_COUNT = 26 };      // room for 4 ring stages
 
 // ------------------------------------------------------------------ small PTX helpers
 __device__ __forceinline__ void csync() { asm volatile("bar.sync 1, %0;" ::"n"(kCT) : "memory"); }   // the compute warps
-__device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
-    return v;
-}
-// Progress counters (compute -> issuer).  The store is deliberately NOT a release: `st.release.cta` compiles to
-// MEMBAR.ALL.CTA + STS and the membar waits for the signalling warp's outstanding global (stash) stores, ~1k cycles on
-// the critical path of every hand-off.  Ordering is already established: every writer executed fence.proxy.async and
-// the named barrier before thread 0 gets here, so the operand bytes are in shared memory before the counter moves.
-__device__ __forceinline__ void st_release(uint32_t* p, uint32_t v) {
-    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
-}
 // Bounded waits: a protocol bug must fail loudly (trap -> CUDA error -> DFF_ECUDA), never hang the GPU.
+// try_wait without a suspend-time hint returns after a short hardware time-out, so the loops below re-arm it; measured
+// (profiles/r02/README.md): a 0.2 ms hint (NANOSLEEP.SYNCS) removes the service warps' polling instructions (a third of all
+// instructions executed) but wakes later -- no gain on chignolin, -5 % on trp-cage, whose weight stream lives on wake-up latency.
 constexpr uint32_t kSpinLimit = 1u << 27;
-__device__ __noinline__ void watchdog_fail(int tag) {
+static __device__ __noinline__ void watchdog_fail(int tag) {
     printf("dff_fused_tc_kernel watchdog: wait %d never completed (block %d, thread %d)\n", tag, (int)blockIdx.x, (int)threadIdx.x);
     __trap();
 }
@@ -167,11 +166,6 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity, int tag) {
     uint32_t n = 0;
     while (!mbar_try(bar, parity))
-        if (++n > kSpinLimit) watchdog_fail(tag);
-}
-__device__ __forceinline__ void spin_until(const uint32_t* ctr, uint32_t target, int tag) {
-    uint32_t n = 0;
-    while (ld_acquire(ctr) < target)
         if (++n > kSpinLimit) watchdog_fail(tag);
 }
 // Optional wait-time accounting (-DDFF_TC_PROFILE): cycles spent in each kind of wait, per CTA, written to T.dbg.
@@ -259,8 +253,6 @@ struct Ctx2 {
     float *sN, *sNh, *sQKV, *sO, *sP, *sDS, *sX, *sV, *sDX, *sTmp;
     float *nhat_hi, *nhat_lo, *slot_hi, *slot_lo;
     uint64_t* bars;
-    uint32_t* posted;      // compute -> issuer: number of operands made ready
-    uint32_t* drained;     // compute -> issuer: number of double-buffered accumulators read back
     uint32_t tmem;
     uint32_t n_post, n_drain, n_acc, n_d1, n_slot;   // identical in every compute thread
     bool slot_held;
@@ -281,8 +273,8 @@ struct Ctx2 {
         fence_proxy_async();
         tc::fence_before_sync();
         csync();
+        if (threadIdx.x == 0) mbar_arrive(bars + B_POST + (n_post & 7u));      // post number n_post -> ring slot n_post & 7
         ++n_post;
-        if (threadIdx.x == 0) st_release(posted, n_post);
     }
     // wait for the double-buffered accumulator of the next QKV / d o job; returns its buffer index
     __device__ __forceinline__ int dq_wait() {
@@ -296,8 +288,8 @@ struct Ctx2 {
     __device__ __forceinline__ void dq_release() {      // accumulator read back (and its smem copy written)
         tc::fence_before_sync();
         csync();
+        if (threadIdx.x == 0) mbar_arrive(bars + B_DRAIN + (n_drain & 1u));    // buffer n_drain & 1 is free again
         ++n_drain;
-        if (threadIdx.x == 0) st_release(drained, n_drain);
     }
     __device__ __forceinline__ void acc_wait() { TCP_BEGIN(); mbar_wait_wd(bars + B_ACC, n_acc & 1u, 2); TCP_END(tw, 1); ++n_acc; tc::fence_after_sync(); }
     __device__ __forceinline__ void d1_wait() { TCP_BEGIN(); mbar_wait_wd(bars + B_D1, n_d1 & 1u, 3); TCP_END(tw, 2); ++n_d1; tc::fence_after_sync(); }
@@ -516,16 +508,12 @@ __device__ __forceinline__ void ln_backward_rows_tc(float* sN, const float* sD, 
 }
 
 // ------------------------------------------------------------------ attention contractions: warp-level tensor-core tiles
-#ifndef DFF_TC_ATTN_SIMT
-#define DFF_TC_ATTN_SIMT 0      // 1: the round-1 CUDA-core attention routines (A/B reference builds only)
-#endif
 }  // namespace v2
 }  // namespace dff
 #include "dff_attn_mma.cuh"
 namespace dff {
 namespace v2 {
 
-#if DFF_TC_ATTN_SIMT
 // ------------------------------------------------------------------ row-local attention (a group of LPR lanes owns one node row)
 // LPR = 16 lanes per row for N <= 16 beads (two rows per warp), 32 for N <= 32.  Inside a group the lane index is the key
 // index j while logits / probabilities are formed and the output-column group (DPL = 64 / LPR columns) while values are
@@ -1346,7 +1334,6 @@ __device__ __forceinline__ void attn_backward_dkv_quads(Ctx2& c, const LayerDev&
     }
 }
 
-#endif  // DFF_TC_ATTN_SIMT
 
 // FF hidden block [rows][4H] TMEM -> shared (row stride LDF), so that the GELU phases can be spread over all threads
 constexpr int kLDF = 256 + 4;
@@ -1399,19 +1386,21 @@ __device__ void forward_pass_tc(const ModelDev& M, Ctx2& c, float t_norm) {
                 }
                 c.mark(2);
             }
-#if DFF_TC_ATTN_SIMT
-            // logits, softmax, P V' - A x_i + c -> canonical operand of the out-projection (row-local, no barrier inside)
-            if (c.quads) attn_forward_quads<C>(c, W, hc, N, NP, st + M.off[ST_P] + (size_t)hc * R * NP);
-            else if (c.pairs) attn_forward_pairs<C>(c, W, hc, N, NP, st + M.off[ST_P] + (size_t)hc * R * NP);
-            else attn_forward_rows<C>(c, W, hc, N, NP, st + M.off[ST_P] + (size_t)hc * R * NP);
-#else
-            {   // logits (HMMA tiles) -> softmax (row-local) -> P V' - A x_i + c (HMMA tiles) -> canonical operand of the out-projection
+            if constexpr (!C::kAttMma) {
+                // logits, softmax, P V' - A x_i + c -> canonical operand of the out-projection (row-local, no barrier inside)
+                if (c.quads) attn_forward_quads<C>(c, W, hc, N, NP, st + M.off[ST_P] + (size_t)hc * R * NP);
+                else if (c.pairs) attn_forward_pairs<C>(c, W, hc, N, NP, st + M.off[ST_P] + (size_t)hc * R * NP);
+                else attn_forward_rows<C>(c, W, hc, N, NP, st + M.off[ST_P] + (size_t)hc * R * NP);
+            } else {
+                // logits (HMMA items) | softmax (rows) | P V' - A x_i + c (HMMA items) -> canonical operand of the out-projection
                 const AttnGeo G(N, NP, c.S_act);
-                attn_logits_mma<C>(c.sQKV, c.sP, G);
+                attn_logits_items<C>(c.sQKV, c.sP, G);
                 csync();
+                c.mark(23);
                 attn_softmax_rows(c.sP, st + M.off[ST_P] + (size_t)hc * R * NP, G);
                 csync();
-                attn_weighted_mma<C>(c.sP, c.sQKV, C::LDQ, 128, G, [&](int row, int col, float v0, float v1) {
+                c.mark(24);
+                attn_weighted_items<C>(c.sP, c.sQKV, C::LDQ, 128, G, [&](int row, int col, float v0, float v1) {
                     const int gc = hc * 64 + col;
                     const float2 cv = __ldg(reinterpret_cast<const float2*>(W.cvec + gc));
                     const float4 e0 = __ldg(reinterpret_cast<const float4*>(W.A + gc * 4)), e1 = __ldg(reinterpret_cast<const float4*>(W.A + gc * 4 + 4));
@@ -1422,7 +1411,6 @@ __device__ void forward_pass_tc(const ModelDev& M, Ctx2& c, float t_norm) {
                     can_store2<C::kCS>(c.slot_hi, c.slot_lo, row, col, v0, v1);
                 });
             }
-#endif
             c.mark(3);
             c.slot_post();
             c.mark(4);
@@ -1613,40 +1601,44 @@ __device__ void backward_pass_tc(const ModelDev& M, Ctx2& c) {
                 c.dq_release();
                 c.mark(16);
             }
-#if DFF_TC_ATTN_SIMT
-            if (c.quads) attn_backward_ds_dq_quads<C>(c, N, NP, l > 0);
-            else if (c.pairs) attn_backward_ds_dq_pairs<C>(c, N, NP, l > 0);
-            else attn_backward_ds_dq<C>(c, N, NP, l > 0);
-            c.mark(17);
-            if (l > 0) c.slot_post(); else csync();          // every ds of the sample is in sDS before the key-row passes
-            c.mark(18);
-            if (c.quads) attn_backward_dkv_quads<C>(c, W, hc, N, NP, l > 0);
-            else if (c.pairs) attn_backward_dkv_pairs<C>(c, W, hc, N, NP, l > 0);
-            else attn_backward_dkv<C>(c, W, hc, N, NP, l > 0);
-            c.mark(19);
-#else
-            {
+            if constexpr (!C::kAttMma) {
+                if (c.quads) attn_backward_ds_dq_quads<C>(c, N, NP, l > 0);
+                else if (c.pairs) attn_backward_ds_dq_pairs<C>(c, N, NP, l > 0);
+                else attn_backward_ds_dq<C>(c, N, NP, l > 0);
+                c.mark(17);
+                if (l > 0) c.slot_post(); else csync();          // every ds of the sample is in sDS before the key-row passes
+                c.mark(18);
+                if (c.quads) attn_backward_dkv_quads<C>(c, W, hc, N, NP, l > 0);
+                else if (c.pairs) attn_backward_dkv_pairs<C>(c, W, hc, N, NP, l > 0);
+                else attn_backward_dkv<C>(c, W, hc, N, NP, l > 0);
+                c.mark(19);
+            } else {
                 const AttnGeo G(N, NP, c.S_act);
-                attn_dp_uw_mma<C>(c.sQKV, c.sO, c.sDS, W.A, hc, G);       // dp, u = A^T q, w = A^T do (HMMA tiles)
+                attn_dp_uw_items<C>(c.sQKV, c.sO, c.sDS, W.A, hc, G);     // dp, u = A^T q, w = A^T do (HMMA items)
                 csync();
+                c.mark(25);
                 attn_ds_rows(c.sP, c.sDS, G);
                 csync();
                 c.mark(17);
-                attn_dx_rows<C>(c.sQKV, c.sO, c.sP, c.sDS, c.sDX, G);     // dx from p, ds, u, w: no dk' / dv' needed
+                attn_dx_rows<C>(c.sQKV, c.sO, c.sP, c.sDS, c.sDX, G);     // dx from p, ds, u, w: no dk' / dv' needed for it
+                c.mark(26);
                 if (l > 0) {
-                    attn_grad_to_slot_mma<C, false>(c, c.sDS, c.sQKV, C::LDQ, 64, kAttnScale, G);     // dq  -> job d q
+                    attn_weighted_items<C>(c.sDS, c.sQKV, C::LDQ, 64, G, [&](int row, int col, float v0, float v1) {     // dq -> job d q
+                        c.slot_acquire();
+                        can_store2<C::kCS>(c.slot_hi, c.slot_lo, row, col, kAttnScale * v0, kAttnScale * v1);
+                    });
                     c.slot_post();
                     c.mark(18);
-                    attn_grad_to_slot_mma<C, true>(c, c.sDS, c.sQKV, C::LDQ, 0, kAttnScale, G);       // dk' -> job d k'
+                    attn_keys_to_slot_items<C>(c, c.sDS, c.sQKV, C::LDQ, kAttnScale, G);     // dk' -> job d k'
                     c.slot_post();
-                    attn_grad_to_slot_mma<C, true>(c, c.sP, c.sO, C::LDO, 0, 1.0f, G);                // dv' -> job d v'
+                    c.mark(27);
+                    attn_keys_to_slot_items<C>(c, c.sP, c.sO, C::LDO, 1.0f, G);              // dv' -> job d v'
                     c.slot_post();
                 } else {
                     csync();          // the next head reloads the buffers
                 }
                 c.mark(19);
             }
-#endif
         }
         if (l > 0) {
             c.acc_wait();
@@ -1703,7 +1695,7 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
     const int N = M.N;
 
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::oBar);
-    uint32_t* ctr = reinterpret_cast<uint32_t*>(bars + B_COUNT);     // [0] posted, [1] drained, [2] tmem base
+    uint32_t* ctr = reinterpret_cast<uint32_t*>(bars + B_COUNT);     // [0] tmem base
     TcJob* jobs = reinterpret_cast<TcJob*>(smem + C::oJobs);
     const int njobs = A.need_backward ? T.njobs_all : T.njobs_fwd;
     const uint32_t nslices = A.need_backward ? T.nslice_all : T.nslice_fwd;
@@ -1725,15 +1717,16 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
         for (int i = 0; i < C::kStages; ++i) { mbar_init(bars + B_FULL + i, 1); mbar_init(bars + B_EMPTY + i, 1); }
         mbar_init(bars + B_DQ, 1); mbar_init(bars + B_DQ + 1, 1);
         mbar_init(bars + B_ACC, 1); mbar_init(bars + B_D1, 1); mbar_init(bars + B_SLOT, 1);
-        ctr[0] = 0; ctr[1] = 0;
+        for (int i = 0; i < 8; ++i) mbar_init(bars + B_POST + i, 1);
+        mbar_init(bars + B_DRAIN, 1); mbar_init(bars + B_DRAIN + 1, 1);
         fence_barrier_init();
     }
-    if (warp == 0) tc::tmem_alloc(ctr + 2, kTmemCols);
+    if (warp == 0) tc::tmem_alloc(ctr, kTmemCols);
     fence_proxy_async();
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
-    const uint32_t tmem = ctr[2];
+    const uint32_t tmem = ctr[0];
 
     if (warp == kComputeThreads / 32) {
         // ===================================================== TMA producer: streams the weight slices of every job
@@ -1785,11 +1778,12 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
                     const uint32_t ccol = f2 >> 16;
                     const bool split = ccol != dcol;                 // never set on double-buffered jobs
                     if (wait_post) {
+                        TCP_BEGIN(); mbar_wait_wd(bars + B_POST + (post_seq & 7u), (post_seq >> 3) & 1u, 7); TCP_END(iw, 0);
                         ++post_seq;
-                        TCP_BEGIN(); spin_until(ctr, post_seq, 7); TCP_END(iw, 0);
                     }
                     if (dbuf) {
-                        TCP_BEGIN(); if (dq_idx >= 2) spin_until(ctr + 1, dq_idx - 1, 8); TCP_END(iw, 1);
+                        // buffer dq_idx & 1 is written for the (dq_idx >> 1)-th time: its previous contents must have been read back
+                        TCP_BEGIN(); if (dq_idx >= 2) mbar_wait_wd(bars + B_DRAIN + (dq_idx & 1u), ((dq_idx >> 1) - 1u) & 1u, 8); TCP_END(iw, 1);
                         dcol += (dq_idx & 1u) * n;
                     }
                     tc::fence_after_sync();
@@ -1849,7 +1843,7 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
         c.sP = smem + C::oP; c.sDS = smem + C::oDS; c.sX = smem + C::oX; c.sV = smem + C::oV;
         c.sDX = smem + C::oDX; c.sTmp = smem + C::oTmp;
         c.nhat_hi = smem + C::oNhatHi; c.nhat_lo = smem + C::oNhatLo; c.slot_hi = smem + C::oSlotHi; c.slot_lo = smem + C::oSlotLo;
-        c.bars = bars; c.posted = ctr; c.drained = ctr + 1; c.tmem = tmem;
+        c.bars = bars; c.tmem = tmem;
         c.n_post = c.n_drain = c.n_acc = c.n_d1 = c.n_slot = 0; c.slot_held = false;
         for (int i = 0; i < 8; ++i) c.tw[i] = 0;
         const long long t_begin = clock64();
@@ -1868,20 +1862,12 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
             c.S_act = my_n / my_groups + (g < my_n % my_groups ? 1 : 0);
             s_next += c.S_act;
             c.rows_act = c.S_act * N;
-#if DFF_TC_ATTN_SIMT
 #ifndef DFF_TC_QUADS16
 #define DFF_TC_QUADS16 0
 #endif
             c.quads = (AttnMap<C>::LPR == 32 || DFF_TC_QUADS16) && c.rows_act > kCW * AttnMap<C>::UPW && N >= 4 &&
                       c.S_act * ((N + 3) >> 2) <= kCW * AttnMap<C>::UPW;      // more rows than lane groups, one quad per group
-#ifdef DFF_TC_PAIRS_ALWAYS
-            c.pairs = true;
-#else
             c.pairs = c.rows_act > kCW * AttnMap<C>::UPW;
-#endif
-#else
-            c.quads = c.pairs = false;
-#endif
             for (int idx = tid; idx < R * 3; idx += kCT) {
                 const int r = idx / 3, cc = idx - r * 3;
                 const bool ok = r < c.rows_act;

@@ -111,6 +111,7 @@ __device__ __forceinline__ void issue_3xtf32(uint32_t d_tmem, const float* a_hi,
 
 }  // namespace tc
 
+#ifdef DFF_HOST_TU       // only the host translation unit (dff_b200.cu) carries the validation kernel
 // ------------------------------------------------------------------ standalone validation / throughput kernel
 // D[64 x N] = A[64 x K] * B[N x K]^T (fp32 in, fp32 out, 3xTF32 on tcgen05), repeated `reps` times for timing.
 // One CTA of 128 threads; used by dff_debug_tc_gemm (tests/test_gpu_tc.py).
@@ -173,5 +174,7 @@ dff_tc_gemm_test_kernel(const float* __restrict__ A, const float* __restrict__ B
     __syncthreads();
     if (warp == 0) tc::tmem_free(d_tmem, 256);
 }
+
+#endif  // DFF_HOST_TU
 
 }  // namespace dff
