@@ -85,6 +85,21 @@ int dff_model_create(dff_model_t** out, int device, int num_beads, int hidden, i
  *                     the decoder output itself, forward only; there is no energy output. */
 int dff_model_create_ex(dff_model_t** out, int device, int num_beads, int hidden, int n_layers,
                         const float* const* weights_host, int n_weights, int max_batch, int conservative);
+/* Every network mode of the reference constructor (graph_transformer.py:23-75, 116-140; main_train.py:149-166):
+ *   use_intrinsic_coords : edge features carry x_j - x_i                (edge_embedding input 3, or 4 with distances)
+ *   use_distances        : edge features carry |x_j - x_i|^2            (edge_embedding input 1, or 4 with intrinsic)
+ *   use_abs_coords       : the node input is [onehot_i, x_i, t]         (node_embedding input N + 4): layer 0 depends on x
+ *   neither edge flag    : the edge feature is one constant zero (edge_embedding input 1)
+ * weights_host[0] is then [H, N + 1 + 3 * use_abs_coords] and weights_host[2] is [H, 3 * intrinsic + distances (or 1)].
+ * The squared-distance channel is collapsed like the intrinsic one and runs on the HMMA attention path. */
+typedef struct dff_model_opts {
+    int conservative;
+    int use_intrinsic_coords;
+    int use_distances;
+    int use_abs_coords;
+} dff_model_opts_t;
+int dff_model_create_v2(dff_model_t** out, int device, int num_beads, int hidden, int n_layers,
+                        const float* const* weights_host, int n_weights, int max_batch, const dff_model_opts_t* opts);
 void dff_model_destroy(dff_model_t* m);
 
 /* Shape queries (mirror of the attributes the reference modules expose). */

@@ -220,3 +220,20 @@ def test_pwd_pair_count_matches_triu_indices():
     from dff_b200 import lib
     for N, off in ((10, 3), (5, 1), (56, 3), (20, 19), (7, 7), (3, 5)):
         assert lib().dff_pwd_num_pairs(N, off) == torch.triu_indices(N, N, offset=off).shape[1]
+
+
+def test_mirror_shapes_for_every_network_mode():
+    """GraphTransformer(...) builds the reference's parameter shapes for every mode (graph_transformer.py:53-65) and refuses the
+    one combination the reference cannot evaluate (conservative without any x-dependence)."""
+    from dff_b200 import DffError
+    from models.graph_transformer import GraphTransformer
+    from oracle.weights import synthetic_net_params
+    for intr, dist, absc, cons in [(False, True, True, True), (True, True, False, True), (True, False, True, False), (False, False, True, True),
+                                   (False, False, False, False), (True, False, False, True)]:
+        net = GraphTransformer(9, 64, "cpu", n_layers=2, use_intrinsic_coords=intr, use_abs_coords=absc, use_distances=dist, conservative=cons)
+        in_edge = 3 * intr + dist + (not intr) * (not dist)
+        ref = synthetic_net_params(9, 64, 2, 1, in_edge=in_edge, in_node_extra=3 if absc else 0, out_dim=1 if cons else 3)
+        assert {k: tuple(v.shape) for k, v in net.state_dict().items()} == {k: tuple(v.shape) for k, v in ref.items()}
+        net.load_state_dict(ref)
+    with pytest.raises(DffError, match="does not depend"):
+        GraphTransformer(9, 64, "cpu", n_layers=2, use_intrinsic_coords=False, use_abs_coords=False, use_distances=False, conservative=True)

@@ -110,8 +110,10 @@ def test_abi_error_behaviour():
     with pytest.raises(DffError):
         eng.score(torch.zeros(2, 5, 3), 0.1)                                       # host tensor: no silent CPU path
     bad = synthetic_net_params(5, 64, 1, in_edge=1)
-    with pytest.raises(DffError, match="intrinsic"):
-        ScoreEngine(bad, device="cuda:0")
+    with pytest.raises(DffError, match="edge_embedding has 1 input"):
+        ScoreEngine(bad, device="cuda:0")                                          # flags say intrinsic (3 features), weights say 1
+    with pytest.raises(DffError, match="does not depend on x"):                    # the reference raises here too (graph_transformer.py:157-158)
+        ScoreEngine(bad, device="cuda:0", use_intrinsic_coords=False, use_distances=False, use_abs_coords=False)
 
 
 @pytest.mark.parametrize("batch", [2, 6, 40])
@@ -280,3 +282,82 @@ def test_bench_batch_sizes_vs_oracle(mol, batch):
     # the same samples placed in different CTAs / row groups (other group sizes, other attention routines) agree to rounding
     eps2, _ = eng.score(torch.roll(x, 1, 0).cuda().contiguous(), 0.02)
     assert rel_err(torch.roll(eps2, -1, 0), eps) < 1e-5
+
+
+def _mode_cases():
+    return sorted(load("score_edge_modes.pt").keys())
+
+
+@pytest.mark.parametrize("key", _mode_cases())
+def test_edge_and_node_modes_vs_reference_golden(key):
+    """use_distances / use_intrinsic_coords + use_distances / use_abs_coords / no edge features, conservative
+    and not, against outputs of the unmodified reference (tests/golden/score_edge_modes.pt) and the collapsed fp64 oracle.
+    The squared-distance channel runs on the HMMA attention path, the absolute-coordinate input on both."""
+    from dff_b200 import ScoreEngine
+    from oracle import collapsed_ref, score_ref
+    from oracle.weights import synthetic_net_params
+    c = load("score_edge_modes.pt")[key]
+    p = synthetic_net_params(c["N"], c["H"], c["L"], c["seed"], in_edge=c["in_edge"], in_node_extra=3 if c["use_abs_coords"] else 0,
+                             out_dim=1 if c["conservative"] else 3)
+    kw = dict(use_intrinsic_coords=c["use_intrinsic_coords"], use_distances=c["use_distances"], use_abs_coords=c["use_abs_coords"])
+    eng = ScoreEngine(p, device="cuda:0", max_batch=64, **kw)
+    x = c["x"].cuda().contiguous()
+    eps, en = eng.score(x, c["t_norm"], want_energy=c["conservative"])
+    assert eng.last_config == "tc"
+    assert rel_err(eps, c["forces"]) < FORCE_RTOL, (key, rel_err(eps, c["forces"]))
+    if c["conservative"]:
+        assert rel_err(en, c["energy"]) < FORCE_RTOL, (key, rel_err(en, c["energy"]))
+        f64, e64, _ = collapsed_ref.forward_backward(score_ref.to_dtype(p, torch.float64), c["x"].double(), c["t_norm"], **kw)
+        assert rel_err(eps, f64) < FORCE_RTOL and rel_err(en, e64) < FORCE_RTOL, (key, rel_err(eps, f64))
+
+
+@pytest.mark.parametrize("intr,dist,absc", [(False, True, True), (True, True, False), (True, False, True)])
+def test_modes_on_both_attention_paths_and_bigger_batches(intr, dist, absc, monkeypatch):
+    """The default training configuration (distances + absolute coordinates, main_train.py:149-166) and two more, at batch sizes
+    that walk several row groups per CTA; where the CUDA-core attention applies (no distance channel) both flavours must agree."""
+    from dff_b200 import ScoreEngine
+    from oracle import collapsed_ref, score_ref
+    from oracle.weights import synthetic_net_params
+    N, H, L, B = 12, 64, 2, 333
+    in_edge = 3 * intr + dist + (not intr) * (not dist)
+    p = synthetic_net_params(N, H, L, seed=77, in_edge=in_edge, in_node_extra=3 if absc else 0)
+    kw = dict(use_intrinsic_coords=intr, use_distances=dist, use_abs_coords=absc)
+    x = 0.8 * torch.randn(B, N, 3, generator=torch.Generator().manual_seed(9))
+    x = x - x.mean(1, keepdim=True)
+    idx = list(range(0, B, 37)) + [B - 1]
+    f64, e64, _ = collapsed_ref.forward_backward(score_ref.to_dtype(p, torch.float64), x[idx].double(), 0.1, **kw)
+    outs = {}
+    for att in (("mma",) if dist else ("mma", "simt")):
+        monkeypatch.setenv("DFF_ATTN", att)
+        eng = ScoreEngine(p, device="cuda:0", max_batch=B, **kw)
+        eps, en = eng.score(x.cuda(), 0.1, want_energy=True)
+        assert rel_err(eps[idx], f64) < FORCE_RTOL and rel_err(en[idx], e64) < FORCE_RTOL, (att, rel_err(eps[idx], f64))
+        outs[att] = eps.cpu()
+    if len(outs) == 2:
+        assert rel_err(outs["mma"], outs["simt"]) < FORCE_RTOL
+
+
+def test_mirror_module_every_mode_and_sampling():
+    """models.GraphTransformer no longer refuses the other modes: the default training configuration loads a state dict with
+    the reference's shapes, matches the reference's forces through the module API and drives a fused DDPM step."""
+    from dff_b200 import SCHED_KEYS
+    from models.graph_transformer import GraphTransformer
+    from oracle import sampler_ref, score_ref
+    from oracle.weights import synthetic_net_params
+    c = load("score_edge_modes.pt")["i0d1a1_c1_N10_H64_L3"]
+    net = GraphTransformer(10, 64, "cuda", n_layers=3, use_intrinsic_coords=False, use_abs_coords=True, use_distances=True, conservative=True).eval()
+    p = synthetic_net_params(10, 64, 3, c["seed"], in_edge=1, in_node_extra=3)
+    net.load_state_dict(p)
+    assert net.node_embedding.weight.shape == (64, 14) and net.edge_embedding.weight.shape == (64, 1)
+    out = net(c["x"].cuda(), torch.eye(10), torch.full((c["x"].shape[0],), c["t_norm"]))
+    assert rel_err(out, c["forces"]) < FORCE_RTOL
+    kw = dict(use_intrinsic_coords=False, use_distances=True, use_abs_coords=True)
+    sched = sampler_ref.cosine_schedule(1000)
+    noise = torch.randn(2, *c["x"].shape, generator=torch.Generator().manual_seed(5))
+    xc = c["x"] - c["x"].mean(1, keepdim=True)
+    ref = xc
+    for s in range(2):
+        ref = sampler_ref.ddpm_step(lambda xx, tn: score_ref.score_forward(p, xx, tn, **kw), sched, ref, 400 - s, 1000, noise[s])
+    xd = xc.cuda().contiguous()
+    net.engine(xd.shape[0]).ddpm_steps(xd, 400, 2, 1000, [sched[k].cuda().contiguous() for k in SCHED_KEYS], noise=noise.cuda().contiguous())
+    assert rel_err(xd, ref) < 2e-4

@@ -168,12 +168,13 @@ __device__ __forceinline__ void keys_dot_cols(float (&acc)[2][4], const float* w
     }
 }
 
-// 16 x 8 tile  rows[16 x 64] * edge[64 x 4]:  u = A_h^T q  or  w = A_h^T do  (columns 0..2; column 3 is zero)
-__device__ __forceinline__ void rows_dot_edge(float (&acc)[4], const float* abuf, int lda, const float* __restrict__ Aedge, int hc, int r0, int m0, int N) {
+// 16 x 8 tile  rows[16 x 64] * edge[64 x 4]:  (u, alpha) = (A_h^T q, a_h . q)  or  (w, beta) = (A_h^T do, a_h . do); columns 0..ncol-1
+__device__ __forceinline__ void rows_dot_edge(float (&acc)[4], const float* abuf, int lda, const float* __restrict__ Aedge, int hc, int r0, int m0, int N,
+                                              int ncol) {
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const float* pa0 = abuf + (r0 + min(m0 + g, N - 1)) * lda + t;
     const float* pa1 = abuf + (r0 + min(m0 + g + 8, N - 1)) * lda + t;
-    const bool on = g < 3;
+    const bool on = g < ncol;
     const float* pe = Aedge + (hc * 64 + t) * 4 + (on ? g : 0);
     float e[16];
 #pragma unroll
@@ -194,17 +195,28 @@ __device__ __forceinline__ void rows_dot_edge(float (&acc)[4], const float* abuf
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Forward phase 1: scaled logits  sP[u][j] = s q_u . k'_j   (items: sample x row block x key-tile pair)
+// Forward phase 1: scaled logits  sP[u][j] = s q_u . k'_j   (items: sample x row block x key-tile pair); with the distance
+// channel also (u, alpha)_u = (A_h^T q_u, a_h . q_u) -> sQKV[u][192..195]  (one more item per row block)
 template <class C>
-__device__ __forceinline__ void attn_logits_items(const float* sQKV, float* sP, const AttnGeo& G) {
+__device__ __forceinline__ void attn_logits_items(float* sQKV, float* sP, const float* __restrict__ Aedge, int hc, bool dist, const AttnGeo& G) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    const int per = G.MB * G.NKP, items = G.S_act * per;
+    const int ipb = G.NKP + (dist ? 1 : 0);                  // items per row block
+    const int per = G.MB * ipb, items = G.S_act * per;
     for (int it = warp; it < items; it += kCW) {
-        const int s = it / per, rem = it - s * per, mb = rem / G.NKP, np = rem - mb * G.NKP;
+        const int s = it / per, rem = it - s * per, mb = rem / ipb, np = rem - mb * ipb;
         const int r0 = s * G.N, m0 = mb * 16, n0 = np * 16;
+        const int ra = m0 + g, rb = ra + 8;
+        if (np == G.NKP) {
+            float e4[4];
+            rows_dot_edge(e4, sQKV, C::LDQ, Aedge, hc, r0, m0, G.N, 4);
+            if (t < 2) {
+                if (ra < G.N) *reinterpret_cast<float2*>(sQKV + (r0 + ra) * C::LDQ + 192 + 2 * t) = make_float2(e4[0], e4[1]);
+                if (rb < G.N) *reinterpret_cast<float2*>(sQKV + (r0 + rb) * C::LDQ + 192 + 2 * t) = make_float2(e4[2], e4[3]);
+            }
+            continue;
+        }
         float c[2][4];
         rows_dot_rows<2>(c, sQKV, C::LDQ, 0, sQKV, C::LDQ, 64, r0, m0, G.N, min(2, G.NK - 2 * np), n0);
-        const int ra = m0 + g, rb = ra + 8;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const int col = n0 + j * 8 + 2 * t;
@@ -215,14 +227,28 @@ __device__ __forceinline__ void attn_logits_items(const float* sQKV, float* sP, 
         }
     }
 }
+// squared distance of rows r and r0 + key (sX holds the centred coordinates, 4 floats per row)
+__device__ __forceinline__ float dist2(const float* sX, int r, int rk) {
+    const float dx = sX[r * 4] - sX[rk * 4], dy = sX[r * 4 + 1] - sX[rk * 4 + 1], dz = sX[r * 4 + 2] - sX[rk * 4 + 2];
+    return dx * dx + dy * dy + dz * dz;
+}
 // Forward phase 2: softmax over the keys of the row's sample, in place; p -> stash.  One warp per row, lane = key (and key + 32).
-__device__ __forceinline__ void attn_softmax_rows(float* sP, float* st_p, const AttnGeo& G) {
+// Distance channel: logit_uj += s alpha_u |x_u - x_j|^2  and  z_u = sum_j p_uj |x_u - x_j|^2 -> sZ[u * ldz]
+template <class C>
+__device__ __forceinline__ void attn_softmax_rows(float* sP, float* st_p, const float* sQKV, const float* sX, float* sZ, int ldz, bool dist, const AttnGeo& G) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rows = G.S_act * G.N;
     for (int r = warp; r < rows; r += kCW) {
         float* row = sP + r * G.NP;
+        const int r0 = (r / G.N) * G.N;
         const bool a0 = lane < G.N, a1 = lane + 32 < G.N;
-        const float l0 = a0 ? row[lane] : -INFINITY, l1 = a1 ? row[lane + 32] : -INFINITY;
+        float l0 = a0 ? row[lane] : -INFINITY, l1 = a1 ? row[lane + 32] : -INFINITY;
+        float d0 = 0.f, d1 = 0.f;
+        if (dist) {
+            const float sa = kAttnScale * sQKV[r * C::LDQ + 195];
+            if (a0) { d0 = dist2(sX, r, r0 + lane); l0 = fmaf(sa, d0, l0); }
+            if (a1) { d1 = dist2(sX, r, r0 + lane + 32); l1 = fmaf(sa, d1, l1); }
+        }
         float m = fmaxf(l0, l1);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -231,6 +257,10 @@ __device__ __forceinline__ void attn_softmax_rows(float* sP, float* st_p, const 
         const float p0 = e0 * inv, p1 = e1 * inv;
         if (lane < G.NP) { row[lane] = p0; st_p[(size_t)r * G.NP + lane] = p0; }
         if (lane + 32 < G.NP) { row[lane + 32] = p1; st_p[(size_t)r * G.NP + lane + 32] = p1; }
+        if (dist) {
+            const float z = warp_sum(p0 * d0 + p1 * d1);
+            if (lane == 0) sZ[r * ldz] = z;
+        }
     }
 }
 // Forward phase 3 / reverse dq phase: 16 x 16 blocks of  W[rows x keys] * B[keys x 64]  -> f_store(row, col, v0, v1)
@@ -254,7 +284,8 @@ __device__ __forceinline__ void attn_weighted_items(const float* sW, const float
     }
 }
 
-// Reverse phase 1: dp_uj = do_u . v'_j -> sDS (raw);  u_u = A_h^T q_u -> sQKV[u][192..194];  w_u = A_h^T do_u -> sO[u][64..66]
+// Reverse phase 1: dp_uj = do_u . v'_j -> sDS (raw);  (u, alpha)_u = (A_h^T q_u, a_h . q_u) -> sQKV[u][192..195];
+// (w, beta)_u = (A_h^T do_u, a_h . do_u) -> sO[u][64..67]
 template <class C>
 __device__ __forceinline__ void attn_dp_uw_items(float* sQKV, float* sO, float* sDS, const float* __restrict__ Aedge, int hc, const AttnGeo& G) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -281,8 +312,8 @@ __device__ __forceinline__ void attn_dp_uw_items(float* sQKV, float* sO, float* 
             float* dst = is_u ? sQKV : sO;
             const int ld = is_u ? C::LDQ : C::LDO, off = is_u ? 192 : 64;
             float e4[4];
-            rows_dot_edge(e4, dst, ld, Aedge, hc, r0, m0, G.N);
-            if (t < 2) {        // columns 2t, 2t + 1 of the 8-wide tile: (0, 1) and (2, 3); column 3 is zero
+            rows_dot_edge(e4, dst, ld, Aedge, hc, r0, m0, G.N, 4);
+            if (t < 2) {        // columns 2t, 2t + 1 of the 8-wide tile: (u0, u1) and (u2, alpha)  /  (w0, w1) and (w2, beta)
                 if (ra < G.N) *reinterpret_cast<float2*>(dst + (r0 + ra) * ld + off + 2 * t) = make_float2(e4[0], e4[1]);
                 if (rb < G.N) *reinterpret_cast<float2*>(dst + (r0 + rb) * ld + off + 2 * t) = make_float2(e4[2], e4[3]);
             }
@@ -290,23 +321,39 @@ __device__ __forceinline__ void attn_dp_uw_items(float* sQKV, float* sO, float* 
     }
 }
 // Reverse phase 2: ds_uj = p_uj (dp_uj - sum_j p_uj dp_uj), in place in sDS.  One warp per row.
-__device__ __forceinline__ void attn_ds_rows(const float* sP, float* sDS, const AttnGeo& G) {
+// Distance channel: dp_uj += beta_u |x_u - x_j|^2 first;  d alpha_u = s sum_j ds_uj |x_u - x_j|^2 -> sDA[u * 4]
+template <class C>
+__device__ __forceinline__ void attn_ds_rows(const float* sP, float* sDS, const float* sO, const float* sX, float* sDA, bool dist, const AttnGeo& G) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rows = G.S_act * G.N;
     for (int r = warp; r < rows; r += kCW) {
         const float* pr = sP + r * G.NP;
         float* dr = sDS + r * G.NP;
+        const int r0 = (r / G.N) * G.N;
         const bool a0 = lane < G.N, a1 = lane + 32 < G.N;
         const float p0 = a0 ? pr[lane] : 0.f, p1 = a1 ? pr[lane + 32] : 0.f;
-        const float d0 = a0 ? dr[lane] : 0.f, d1 = a1 ? dr[lane + 32] : 0.f;
+        float d0 = a0 ? dr[lane] : 0.f, d1 = a1 ? dr[lane + 32] : 0.f;
+        float q0 = 0.f, q1 = 0.f;
+        if (dist) {
+            const float beta = sO[r * C::LDO + 67];
+            if (a0) { q0 = dist2(sX, r, r0 + lane); d0 = fmaf(beta, q0, d0); }
+            if (a1) { q1 = dist2(sX, r, r0 + lane + 32); d1 = fmaf(beta, q1, d1); }
+        }
         const float tsum = warp_sum(p0 * d0 + p1 * d1);
-        if (lane < G.NP) dr[lane] = p0 * (d0 - tsum);
-        if (lane + 32 < G.NP) dr[lane + 32] = p1 * (d1 - tsum);
+        const float s0 = p0 * (d0 - tsum), s1 = p1 * (d1 - tsum);
+        if (lane < G.NP) dr[lane] = s0;
+        if (lane + 32 < G.NP) dr[lane + 32] = s1;
+        if (dist) {
+            const float da = kAttnScale * warp_sum(s0 * q0 + s1 * q1);
+            if (lane == 0) sDA[r * 4] = da;
+        }
     }
 }
 // Reverse phase 3: dx_j += sum_i (p_ij w_i + s ds_ij u_i) - w_j.  Four lanes per (key row, component), fixed summation order: deterministic.
+// Distance channel: with E_ij = d / d|x_i - x_j|^2 = s ds_ij alpha_i + p_ij beta_i,   dx_j += 2 sum_i (E_ij + E_ji) (x_j - x_i)
 template <class C>
-__device__ __forceinline__ void attn_dx_rows(const float* sQKV, const float* sO, const float* sP, const float* sDS, float* sDX, const AttnGeo& G) {
+__device__ __forceinline__ void attn_dx_rows(const float* sQKV, const float* sO, const float* sP, const float* sDS, const float* sX, float* sDX, bool dist,
+                                             const AttnGeo& G) {
     const int rows = G.S_act * G.N;
     const int q = threadIdx.x & 3;
     for (int base = 0; base < rows * 3; base += kCT / 4) {         // warp-uniform trip count (the quad shuffles need whole warps)
@@ -315,12 +362,19 @@ __device__ __forceinline__ void attn_dx_rows(const float* sQKV, const float* sO,
         const int idx = valid ? idx0 : 0;
         const int j = idx / 3, cc = idx - j * 3;
         const int r0 = (j / G.N) * G.N, jj = j - r0;
-        float acc = 0.f, acd = 0.f;
+        float acc = 0.f, acd = 0.f, ace = 0.f;
+        const float aj = dist ? kAttnScale * sQKV[j * C::LDQ + 195] : 0.f, bj = dist ? sO[j * C::LDO + 67] : 0.f, xj = sX[j * 4 + cc];
         for (int i = q; i < G.N; i += 4) {
-            acc = fmaf(sP[(r0 + i) * G.NP + jj], sO[(r0 + i) * C::LDO + 64 + cc], acc);
-            acd = fmaf(sDS[(r0 + i) * G.NP + jj], sQKV[(r0 + i) * C::LDQ + 192 + cc], acd);
+            const float pij = sP[(r0 + i) * G.NP + jj], dij = sDS[(r0 + i) * G.NP + jj];
+            acc = fmaf(pij, sO[(r0 + i) * C::LDO + 64 + cc], acc);
+            acd = fmaf(dij, sQKV[(r0 + i) * C::LDQ + 192 + cc], acd);
+            if (dist) {
+                const float e = fmaf(kAttnScale * sQKV[(r0 + i) * C::LDQ + 195], dij, sO[(r0 + i) * C::LDO + 67] * pij)       // E_ij
+                              + fmaf(aj, sDS[j * G.NP + i], bj * sP[j * G.NP + i]);                                          // E_ji
+                ace = fmaf(e, xj - sX[(r0 + i) * 4 + cc], ace);
+            }
         }
-        float v = acc + kAttnScale * acd;
+        float v = acc + kAttnScale * acd + 2.0f * ace;
         v += __shfl_xor_sync(0xffffffffu, v, 1);
         v += __shfl_xor_sync(0xffffffffu, v, 2);
         if (valid && q == 0) sDX[j * 4 + cc] += v - sO[j * C::LDO + 64 + cc];

@@ -71,6 +71,7 @@ struct dff_model {
     float* d_sched = nullptr;  size_t d_sched_T = 0;
     int last_R = 0, last_S = 0, last_att = 0;
     bool attn_mma = false;          // default attention flavour of the tcgen05 kernel for this model (set at create)
+    bool modes_default = true;      // intrinsic coordinates only (what the mma.sync fallback kernel implements)
     const char* last_cfg = "none";
     // tcgen05 configuration (hidden = 64): job table + canonical hi/lo weight panels
     bool tc_ok = false;
@@ -194,6 +195,9 @@ int launch(dff_model* m, StepArgs& A, cudaStream_t stream) {
         else if (!strcmp(e, "duo") && s32 >= 1 && kThreads == 256) cfg = DUO;
         else if (!strcmp(e, "tc") && m->tc_ok) cfg = TC;
     }
+    if (cfg != TC && !m->modes_default)
+        return fail(DFF_EINVAL, "the distance / absolute-coordinate network modes run on the tcgen05 kernel only (hidden 64 up to 64 beads, "
+                                "hidden 96 / 128 up to 56 beads); this shape falls back to the mma.sync kernel, which implements intrinsic coordinates only");
     if (cfg == TC) {
         // tcgen05 kernel: 64-row passes (MMA M = 64), 1 head per chunk, 1 CTA/SM
         const int S = std::min(s64, std::max(need1, 1));
@@ -208,6 +212,7 @@ int launch(dff_model* m, StepArgs& A, cudaStream_t stream) {
         // attention flavour: HMMA tiles (general path: every edge mode, the large-N nets) or the CUDA-core routines (small intrinsic nets)
         int att = m->attn_mma ? 1 : 0;
         if (const char* e = getenv("DFF_ATTN")) att = !strcmp(e, "mma") ? 1 : (!strcmp(e, "simt") ? 0 : att);
+        if (M.edge_dist) att = 1;          // no CUDA-core implementation of the squared-distance channel
         m->last_cfg = att ? "tc" : "tc";
         m->last_att = att;
         int PN, R = 64;
@@ -277,8 +282,22 @@ int dff_model_create(dff_model_t** out, int device, int num_beads, int hidden, i
 
 int dff_model_create_ex(dff_model_t** out, int device, int num_beads, int hidden, int n_layers,
                         const float* const* w, int n_weights, int max_batch, int conservative) {
+    dff_model_opts_t o{conservative, 1, 0, 0};
+    return dff_model_create_v2(out, device, num_beads, hidden, n_layers, w, n_weights, max_batch, &o);
+}
+
+int dff_model_create_v2(dff_model_t** out, int device, int num_beads, int hidden, int n_layers,
+                        const float* const* w, int n_weights, int max_batch, const dff_model_opts_t* opts) {
     if (!out) return fail(DFF_EINVAL, "out is NULL");
     *out = nullptr;
+    if (!opts) return fail(DFF_EINVAL, "opts is NULL");
+    const int conservative = opts->conservative ? 1 : 0;
+    const bool intr = opts->use_intrinsic_coords != 0, dist = opts->use_distances != 0, absc = opts->use_abs_coords != 0;
+    if (conservative && !intr && !dist && !absc)
+        return fail(DFF_EINVAL, "a conservative network without intrinsic coordinates, distances or absolute coordinates does not depend on x: "
+                                "the reference raises 'Gradient after computing forces is None' (graph_transformer.py:157-158)");
+    const int in_edge = 3 * intr + dist + ((!intr && !dist) ? 1 : 0);       // graph_transformer.py:54-58
+    const int in_node = num_beads + 1 + (absc ? 3 : 0);                       // :53
     const int N = num_beads, H = hidden, L = n_layers;
     if (N < 2 || N > kMaxBeads) return fail(DFF_EINVAL, "num_beads %d unsupported (2..%d)", N, kMaxBeads);
     if (H < 32 || H > 128 || H % 32) return fail(DFF_EINVAL, "hidden %d unsupported (32, 64, 96, 128)", H);
@@ -302,6 +321,8 @@ int dff_model_create_ex(dff_model_t** out, int device, int num_beads, int hidden
     m->N = N; m->NP = (N + 3) / 4 * 4; m->H = H; m->HP = (H <= 64) ? 64 : 128; m->L = L; m->nch = 4 * H / 128;
     m->max_batch = max_batch;
     m->conservative = conservative ? 1 : 0;
+    m->modes_default = intr && !dist && !absc;
+    m->attn_mma = dist;                      // the squared-distance channel lives in the HMMA attention path
     const int HP = m->HP, nch = m->nch;
     if ((4 * H) % 128) { delete m; return fail(DFF_EINVAL, "4*hidden must be a multiple of 128"); }
 
@@ -312,10 +333,13 @@ int dff_model_create_ex(dff_model_t** out, int device, int num_beads, int hidden
     struct LayerOff { size_t ln1_g, ln1_b, bqkv[2], A, cvec, bo, g1a, g1b, ln2_g, ln2_b, b1, b2, g2a, g2b; };
     std::vector<LayerOff> lo(L);
     const int n_dec = conservative ? 1 : 3;                  // node_decoder rows: Linear(H, 1) or Linear(H, 3)
-    const size_t o_emb = P.alloc((size_t)N * H), o_embt = P.alloc(H), o_dec = P.alloc((size_t)n_dec * H);
+    const size_t o_emb = P.alloc((size_t)N * H), o_embt = P.alloc(H), o_dec = P.alloc((size_t)n_dec * H), o_embx = P.alloc((size_t)3 * H);
     for (int i = 0; i < N; ++i)
-        for (int d = 0; d < H; ++d) P.buf[o_emb + (size_t)i * H + d] = Wn[(size_t)d * (N + 1) + i] + bn[d];
-    for (int d = 0; d < H; ++d) P.buf[o_embt + d] = Wn[(size_t)d * (N + 1) + N];
+        for (int d = 0; d < H; ++d) P.buf[o_emb + (size_t)i * H + d] = Wn[(size_t)d * in_node + i] + bn[d];
+    for (int d = 0; d < H; ++d) P.buf[o_embt + d] = Wn[(size_t)d * in_node + in_node - 1];
+    if (absc)                       // node input [onehot_i, x_i, t] (graph_transformer.py:99-100): columns N .. N + 2 act on x_i
+        for (int c2 = 0; c2 < 3; ++c2)
+            for (int d = 0; d < H; ++d) P.buf[o_embx + (size_t)c2 * H + d] = Wn[(size_t)d * in_node + N + c2];
     for (int d = 0; d < n_dec * H; ++d) P.buf[o_dec + d] = Wd[d];
 
     auto LW = [&](int l, int k) { return w[DFF_NUM_GLOBAL_WEIGHTS + DFF_NUM_LAYER_WEIGHTS * l + k]; };
@@ -348,13 +372,16 @@ int dff_model_create_ex(dff_model_t** out, int device, int num_beads, int hidden
         }
         // fold edge_embedding into edges_to_kv (exact: no nonlinearity between them, graph_transformer.py:96,235,288)
         for (int j = 0; j < 512; ++j) {
-            double a[3] = {0, 0, 0}, cc = bekv[j];
+            double a[4] = {0, 0, 0, 0}, cc = bekv[j];
             for (int k = 0; k < H; ++k) {
                 const double wk = Wekv[(size_t)j * H + k];
-                a[0] += wk * We[k * 3 + 0]; a[1] += wk * We[k * 3 + 1]; a[2] += wk * We[k * 3 + 2];
+                for (int e = 0; e < in_edge; ++e) a[e] += wk * We[(size_t)k * in_edge + e];
                 cc += wk * be[k];
             }
-            P.buf[o.A + j * 4 + 0] = (float)a[0]; P.buf[o.A + j * 4 + 1] = (float)a[1]; P.buf[o.A + j * 4 + 2] = (float)a[2];
+            // columns of the folded map: x_j - x_i (intrinsic) and |x_j - x_i|^2 (distances); the placeholder zero feature has none
+            const double ad = (intr && dist) ? a[3] : (dist ? a[0] : 0.0);
+            for (int e = 0; e < 3; ++e) P.buf[o.A + j * 4 + e] = intr ? (float)a[e] : 0.f;
+            P.buf[o.A + j * 4 + 3] = (float)ad;
             P.buf[o.cvec + j] = (float)cc;
         }
     }
@@ -511,7 +538,7 @@ int dff_model_create_ex(dff_model_t** out, int device, int num_beads, int hidden
             };
             jdo(0, TCJ_WAIT_POST); jdo(1, 0);
             for (int hc = 0; hc < 8; ++hc) {
-                if (l > 0) {
+                if (l > 0 || absc) {
                     // d n_hat = dq Wq + dk' Wk + dv' Wv accumulates over the 8 head chunks in THREE TMEM accumulators (one per
                     // product) that the epilogue adds in fp32: the tensor core's accumulation chain is 192 MMAs long instead of
                     // 576 (its accumulate rounding is what separates this kernel's error from the reference's own)
@@ -542,7 +569,7 @@ int dff_model_create_ex(dff_model_t** out, int device, int num_beads, int hidden
     }
 
 
-    if (tc_shape && (int)tcj.size() <= v2::kJobCap) {
+    if (tc_shape) {      // job tables longer than the shared-memory cache (v2::kJobCap) are read from global memory past the cap
         std::vector<v2::TcJob> hj(tcj.size());
         for (size_t i = 0; i < hj.size(); ++i) { hj[i] = tcj[i].j; hj[i].w_off = (uint32_t)tcj[i].offset; }
         if (cudaMalloc(&m->d_jobs, hj.size() * sizeof(v2::TcJob)) != cudaSuccess) { cleanup(); return fail(DFF_ENOMEM, "cudaMalloc jobs failed"); }
@@ -570,6 +597,7 @@ int dff_model_create_ex(dff_model_t** out, int device, int num_beads, int hidden
         M.N = N; M.NP = m->NP; M.H = H; M.L = L; M.S = 1; M.nch = nch;
         M.emb = m->d_weights + o_emb; M.embt = m->d_weights + o_embt; M.dec_w = m->d_weights + o_dec; M.dec_b = bd[0];
         M.conservative = m->conservative;
+        M.edge_dist = dist ? 1 : 0; M.abs_coords = absc ? 1 : 0; M.embx = m->d_weights + o_embx;
         for (int i = 0; i < 3; ++i) M.dec_b3[i] = conservative ? 0.f : bd[i];
         for (int l = 0; l < L; ++l) {
             const LayerOff& o = lo[l];

@@ -33,7 +33,8 @@ struct Seg {
 struct LayerDev {
     const float* ln1_g; const float* ln1_b;
     const float* bqkv;      // [8][192]  per head: q bias | k bias | v bias
-    const float* A;         // [8][64][4] folded edge map rows (a0,a1,a2,0): A = W_ekv W_e
+    const float* A;         // [8][64][4] folded edge map rows (a0,a1,a2,a): A = W_ekv W_e columns acting on x_j - x_i (0 without
+                            // intrinsic coordinates) and a = the column acting on |x_j - x_i|^2 (0 without distances)
     const float* cvec;      // [512]     c = W_ekv b_e + b_ekv
     const float* bo;        // [HP]
     const float* g1a; const float* g1b;   // gate 1: (w_a + w_c), (w_b - w_c)   [H]
@@ -62,6 +63,10 @@ struct ModelDev {
     long long scratch_per_cta;      // floats
     long long layer_floats;
     long long off[ST_COUNT];
+    // edge / node input modes (graph_transformer.py:53-58, 99-100, 116-140)
+    int edge_dist;                  // 1: the edge features carry |x_j - x_i|^2 (use_distances)
+    int abs_coords;                 // 1: the node input carries x_i (use_abs_coords): layer 0 depends on x
+    const float* embx;              // [3][H]  W_n[:, N + c] (abs_coords only)
 };
 
 struct StepArgs {

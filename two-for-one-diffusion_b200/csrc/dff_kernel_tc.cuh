@@ -1349,7 +1349,10 @@ __device__ void forward_pass_tc(const ModelDev& M, Ctx2& c, float t_norm) {
     // layer-0 node stream: W_n [onehot_i, t] + b_n   (graph_transformer.py:99-103)
     for (int idx = tid; idx < rows * C::kHP; idx += kCT) {
         const int r = idx / C::kHP, d = idx - r * C::kHP;
-        c.sN[r * C::LDH + d] = (d < H) ? __ldg(M.emb + (r % N) * H + d) + t_norm * __ldg(M.embt + d) : 0.f;
+        float v = (d < H) ? __ldg(M.emb + (r % N) * H + d) + t_norm * __ldg(M.embt + d) : 0.f;
+        if (M.abs_coords && d < H)        // node input [onehot_i, x_i, t] (graph_transformer.py:99-100)
+            v += c.sX[r * 4] * __ldg(M.embx + d) + c.sX[r * 4 + 1] * __ldg(M.embx + H + d) + c.sX[r * 4 + 2] * __ldg(M.embx + 2 * H + d);
+        c.sN[r * C::LDH + d] = v;
     }
     // augmented operand columns of this step: [x0 x1 x2 1] (chunk H/4); chunk H/4 + 1 stays zero
     if (tid < R) {
@@ -1394,10 +1397,11 @@ __device__ void forward_pass_tc(const ModelDev& M, Ctx2& c, float t_norm) {
             } else {
                 // logits (HMMA items) | softmax (rows) | P V' - A x_i + c (HMMA items) -> canonical operand of the out-projection
                 const AttnGeo G(N, NP, c.S_act);
-                attn_logits_items<C>(c.sQKV, c.sP, G);
+                const bool dist = M.edge_dist != 0;
+                attn_logits_items<C>(c.sQKV, c.sP, W.A, hc, dist, G);
                 csync();
                 c.mark(23);
-                attn_softmax_rows(c.sP, st + M.off[ST_P] + (size_t)hc * R * NP, G);
+                attn_softmax_rows<C>(c.sP, st + M.off[ST_P] + (size_t)hc * R * NP, c.sQKV, c.sX, c.sO + 64, C::LDO, dist, G);     // z -> sO pad (free in the forward pass)
                 csync();
                 c.mark(24);
                 attn_weighted_items<C>(c.sP, c.sQKV, C::LDQ, 128, G, [&](int row, int col, float v0, float v1) {
@@ -1407,6 +1411,7 @@ __device__ void forward_pass_tc(const ModelDev& M, Ctx2& c, float t_norm) {
                     const float x0 = c.sX[row * 4], x1 = c.sX[row * 4 + 1], x2 = c.sX[row * 4 + 2];
                     v0 += cv.x - (e0.x * x0 + e0.y * x1 + e0.z * x2);
                     v1 += cv.y - (e1.x * x0 + e1.y * x1 + e1.z * x2);
+                    if (dist) { const float z = c.sO[row * C::LDO + 64]; v0 = fmaf(e0.w, z, v0); v1 = fmaf(e1.w, z, v1); }     // + a_h z_i
                     c.slot_acquire();      // the previous out-projection has had the whole head to finish reading the slot
                     can_store2<C::kCS>(c.slot_hi, c.slot_lo, row, col, v0, v1);
                 });
@@ -1516,6 +1521,7 @@ __device__ void backward_pass_tc(const ModelDev& M, Ctx2& c) {
     for (int l = M.L - 1; l >= 0; --l) {
         const LayerDev& W = M.layer[l];
         float* st = c.stash + (size_t)l * M.layer_floats;
+        const bool deep = l > 0 || M.abs_coords != 0;      // the layer's input nodes depend on x: dq / dk' / dv' feed d n_hat
 
         // gated residual 2 backward: d ff -> canonical operand, d m (partial) -> sN
         gate_backward_rows_can<C>(c.sN, nullptr, c.nhat_hi, c.nhat_lo, H, rows, nullptr, nullptr, nullptr, st + M.off[ST_FF],
@@ -1602,30 +1608,36 @@ __device__ void backward_pass_tc(const ModelDev& M, Ctx2& c) {
                 c.mark(16);
             }
             if constexpr (!C::kAttMma) {
-                if (c.quads) attn_backward_ds_dq_quads<C>(c, N, NP, l > 0);
-                else if (c.pairs) attn_backward_ds_dq_pairs<C>(c, N, NP, l > 0);
-                else attn_backward_ds_dq<C>(c, N, NP, l > 0);
+                if (c.quads) attn_backward_ds_dq_quads<C>(c, N, NP, deep);
+                else if (c.pairs) attn_backward_ds_dq_pairs<C>(c, N, NP, deep);
+                else attn_backward_ds_dq<C>(c, N, NP, deep);
                 c.mark(17);
-                if (l > 0) c.slot_post(); else csync();          // every ds of the sample is in sDS before the key-row passes
+                if (deep) c.slot_post(); else csync();          // every ds of the sample is in sDS before the key-row passes
                 c.mark(18);
-                if (c.quads) attn_backward_dkv_quads<C>(c, W, hc, N, NP, l > 0);
-                else if (c.pairs) attn_backward_dkv_pairs<C>(c, W, hc, N, NP, l > 0);
-                else attn_backward_dkv<C>(c, W, hc, N, NP, l > 0);
+                if (c.quads) attn_backward_dkv_quads<C>(c, W, hc, N, NP, deep);
+                else if (c.pairs) attn_backward_dkv_pairs<C>(c, W, hc, N, NP, deep);
+                else attn_backward_dkv<C>(c, W, hc, N, NP, deep);
                 c.mark(19);
             } else {
                 const AttnGeo G(N, NP, c.S_act);
-                attn_dp_uw_items<C>(c.sQKV, c.sO, c.sDS, W.A, hc, G);     // dp, u = A^T q, w = A^T do (HMMA items)
+                const bool dist = M.edge_dist != 0;
+                attn_dp_uw_items<C>(c.sQKV, c.sO, c.sDS, W.A, hc, G);     // dp, (u, alpha), (w, beta) (HMMA items)
                 csync();
                 c.mark(25);
-                attn_ds_rows(c.sP, c.sDS, G);
+                attn_ds_rows<C>(c.sP, c.sDS, c.sO, c.sX, c.sTmp, dist, G);
                 csync();
                 c.mark(17);
-                attn_dx_rows<C>(c.sQKV, c.sO, c.sP, c.sDS, c.sDX, G);     // dx from p, ds, u, w: no dk' / dv' needed for it
+                attn_dx_rows<C>(c.sQKV, c.sO, c.sP, c.sDS, c.sX, c.sDX, dist, G);     // dx from p, ds, u, w (+ the distance channel)
                 c.mark(26);
-                if (l > 0) {
+                if (deep) {
                     attn_weighted_items<C>(c.sDS, c.sQKV, C::LDQ, 64, G, [&](int row, int col, float v0, float v1) {     // dq -> job d q
+                        v0 *= kAttnScale; v1 *= kAttnScale;
+                        if (dist) {            // + d alpha_i a_h
+                            const float da = c.sTmp[row * 4];
+                            v0 = fmaf(da, __ldg(W.A + (hc * 64 + col) * 4 + 3), v0); v1 = fmaf(da, __ldg(W.A + (hc * 64 + col) * 4 + 7), v1);
+                        }
                         c.slot_acquire();
-                        can_store2<C::kCS>(c.slot_hi, c.slot_lo, row, col, kAttnScale * v0, kAttnScale * v1);
+                        can_store2<C::kCS>(c.slot_hi, c.slot_lo, row, col, v0, v1);
                     });
                     c.slot_post();
                     c.mark(18);
@@ -1640,7 +1652,7 @@ __device__ void backward_pass_tc(const ModelDev& M, Ctx2& c) {
                 c.mark(19);
             }
         }
-        if (l > 0) {
+        if (deep) {
             c.acc_wait();
             // d n_hat = (dq Wq) + (dk' Wk) + (dv' Wv): three TMEM accumulators (columns 0, kColD + 128, kColD + 128 + HP), added here
             {
@@ -1682,6 +1694,19 @@ __device__ void backward_pass_tc(const ModelDev& M, Ctx2& c) {
             c.mark(21);
         }
     }
+    if (M.abs_coords) {
+        // node_embedding's x columns (graph_transformer.py:99-103): dx_i += W_n[:, N..N+2]^T d n0_i   (sN = d n0 after layer 0)
+        for (int r = warp_id; r < rows; r += kCW) {
+            float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+            for (int d = lane_id; d < H; d += 32) {
+                const float v = c.sN[r * C::LDH + d];
+                g0 = fmaf(v, __ldg(M.embx + d), g0); g1 = fmaf(v, __ldg(M.embx + H + d), g1); g2 = fmaf(v, __ldg(M.embx + 2 * H + d), g2);
+            }
+            g0 = warp_sum(g0); g1 = warp_sum(g1); g2 = warp_sum(g2);
+            if (lane_id == 0) { c.sDX[r * 4] += g0; c.sDX[r * 4 + 1] += g1; c.sDX[r * 4 + 2] += g2; }
+        }
+        csync();
+    }
 }
 
 // ------------------------------------------------------------------ the kernel
@@ -1711,7 +1736,7 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
 
     for (int idx = tid; idx < C::oW; idx += kTcThreads) smem[idx] = 0.f;             // activations, operands
     for (int idx = C::oX + tid; idx < C::oJobs; idx += kTcThreads) smem[idx] = 0.f;
-    for (int idx = tid; idx < njobs * 4; idx += kTcThreads)
+    for (int idx = tid; idx < min(njobs, kJobCap) * 4; idx += kTcThreads)          // entries past the cache are read from global memory
         reinterpret_cast<uint32_t*>(jobs)[idx] = reinterpret_cast<const uint32_t*>(T.jobs)[idx];
     if (tid == 0) {
         for (int i = 0; i < C::kStages; ++i) { mbar_init(bars + B_FULL + i, 1); mbar_init(bars + B_EMPTY + i, 1); }
@@ -1735,7 +1760,7 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
             long long pw[1] = {0}; (void)pw;
             for (uint32_t rep = 0; rep < reps; ++rep)
                 for (int j = 0; j < njobs; ++j) {
-                    const TcJob jb = jobs[j];
+                    const TcJob jb = j < kJobCap ? jobs[j] : T.jobs[j];
                     const char* src = reinterpret_cast<const char*>(T.wbase + jb.w_off);
                     const uint32_t slice_bytes = (uint32_t)jb.slice_16b * 16u;
                     for (uint32_t s = 0; s < jb.n_slices; ++s, ++slice_i) {
@@ -1768,7 +1793,7 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
             for (uint32_t rep = 0; rep < reps; ++rep)
                 for (int j = 0; j < njobs; ++j) {
                     // job fields, made warp-uniform
-                    const uint32_t* jw = reinterpret_cast<const uint32_t*>(jobs + j);      // words 1..3 of the 16-byte entry
+                    const uint32_t* jw = reinterpret_cast<const uint32_t*>(j < kJobCap ? jobs + j : T.jobs + j);      // words 1..3 of the 16-byte entry
                     const uint32_t f0 = __shfl_sync(0xffffffffu, jw[1], 0), f1 = __shfl_sync(0xffffffffu, jw[2], 0);
                     const uint32_t f2 = __shfl_sync(0xffffffffu, jw[3], 0);
                     const uint32_t n_slices = (f0 >> 16) & 0xffu, ks = f0 >> 24, n = f1 & 0xffffu;

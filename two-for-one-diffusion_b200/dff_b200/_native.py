@@ -23,6 +23,10 @@ class MdParams(C.Structure):
                 ("vscale", C.c_float), ("noisescale", C.c_float), ("beta", C.c_float), ("dtau", C.c_float)]
 
 
+class ModelOpts(C.Structure):
+    _fields_ = [("conservative", C.c_int), ("use_intrinsic_coords", C.c_int), ("use_distances", C.c_int), ("use_abs_coords", C.c_int)]
+
+
 _lib = None
 
 # every symbol include/dff_b200.h declares: name -> (restype, argtypes)
@@ -33,6 +37,7 @@ SYMBOLS = {
     "dff_device_count": (C.c_int, []),
     "dff_model_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp), C.c_int, C.c_int]),
     "dff_model_create_ex": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp), C.c_int, C.c_int, C.c_int]),
+    "dff_model_create_v2": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp), C.c_int, C.c_int, C.POINTER(ModelOpts)]),
     "dff_model_destroy": (None, [_vp]),
     "dff_model_num_beads": (C.c_int, [_vp]),
     "dff_model_hidden": (C.c_int, [_vp]),

@@ -48,15 +48,20 @@ class ScoreEngine:
     """Device-resident packed model.  `state` holds the score-network tensors under the reference's
     state-dict names (`GraphTransformer.state_dict()`, i.e. checkpoint keys minus `ema_model.model.`)."""
 
-    def __init__(self, state: Dict[str, torch.Tensor], device="cuda:0", max_batch: int = 4096):
+    def __init__(self, state: Dict[str, torch.Tensor], device="cuda:0", max_batch: int = 4096, use_intrinsic_coords: bool = True,
+                 use_distances: bool = False, use_abs_coords: bool = False):
         L = count_layers(state)
         H, in_node = state["node_embedding.weight"].shape
         n_out = state["node_decoder.weight"].shape[0]
-        if state["edge_embedding.weight"].shape[1] != 3 or n_out not in (1, 3):
-            raise nat.DffError("only intrinsic-coordinate networks (use_intrinsic_coords=True, use_abs_coords=False, "
-                               "use_distances=False; conservative or not) are supported")
+        in_edge = state["edge_embedding.weight"].shape[1]
+        want_edge = 3 * bool(use_intrinsic_coords) + bool(use_distances) + (not use_intrinsic_coords and not use_distances)
+        if in_edge != want_edge or n_out not in (1, 3):
+            raise nat.DffError(f"edge_embedding has {in_edge} input features, but use_intrinsic_coords={use_intrinsic_coords}, "
+                               f"use_distances={use_distances} needs {want_edge} (graph_transformer.py:54-58); "
+                               "pass the flags the network was trained with (args.pickle)")
         self.conservative = n_out == 1
-        self.num_beads, self.hidden, self.n_layers = in_node - 1, H, L
+        self.use_intrinsic_coords, self.use_distances, self.use_abs_coords = bool(use_intrinsic_coords), bool(use_distances), bool(use_abs_coords)
+        self.num_beads, self.hidden, self.n_layers = in_node - 1 - (3 if use_abs_coords else 0), H, L
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise nat.DffError("ScoreEngine needs a CUDA device; there is no CPU path")
@@ -65,8 +70,8 @@ class ScoreEngine:
         arr = (C.c_void_p * len(host))(*[t.data_ptr() for t in host])
         h = C.c_void_p()
         idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
-        nat.check(nat.lib().dff_model_create_ex(C.byref(h), idx, self.num_beads, H, L, arr, len(host), self.max_batch,
-                                                int(self.conservative)))
+        opts = nat.ModelOpts(int(self.conservative), int(self.use_intrinsic_coords), int(self.use_distances), int(self.use_abs_coords))
+        nat.check(nat.lib().dff_model_create_v2(C.byref(h), idx, self.num_beads, H, L, arr, len(host), self.max_batch, C.byref(opts)))
         self._h = h
         self._flags = torch.zeros(1, dtype=torch.int32, device=self.device)
 

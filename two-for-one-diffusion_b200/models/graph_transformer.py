@@ -1,6 +1,9 @@
 """`GraphTransformer` with the reference's constructor, state-dict layout and forward() contract
 (models/graph_transformer.py:18-114), executed by the fused sm_100a kernel in libdff_b200.so.
 
+Every constructor mode of the reference is supported: use_intrinsic_coords / use_distances (edge features x_j - x_i and
+|x_j - x_i|^2) and use_abs_coords (x_i in the node input), conservative or not (graph_transformer.py:53-65, 99-100, 116-140).
+
 The nn.Module tree below exists ONLY to own parameters under the reference's checkpoint key names
 (`graphtransformer.layers.{l}.0.0.fn.to_q.weight`, ... SURVEY.md 3.4) so `load_state_dict` of a shipped
 `model-best.pt["ema"]` works unchanged.  None of these sub-modules has a forward(): the arithmetic
@@ -67,12 +70,13 @@ class GraphTransformer(nn.Module):
         self.num_beads, self.hidden_nf, self.n_layers = num_beads, hidden_nf, n_layers
         self.use_intrinsic_coords, self.use_distances = use_intrinsic_coords, use_distances
         self.use_abs_coords, self.conservative = use_abs_coords, conservative
-        if not (use_intrinsic_coords and not use_abs_coords and not use_distances):
-            raise DffError("the B200 kernels implement the edge mode of every shipped checkpoint: "
-                           "use_intrinsic_coords=True, use_abs_coords=False, use_distances=False (conservative or not); "
-                           "the distance / absolute-coordinate modes are listed as 'next' in SURVEY.md 8f")
-        self.node_embedding = nn.Linear(num_beads + 1, hidden_nf)
-        self.edge_embedding = nn.Linear(3, hidden_nf)
+        if conservative and not (use_intrinsic_coords or use_abs_coords or use_distances):
+            raise DffError("a conservative network without intrinsic coordinates, distances or absolute coordinates does not depend "
+                           "on x: the reference raises 'Gradient after computing forces is None' (graph_transformer.py:157-158)")
+        in_node_nf = num_beads + 1 + use_abs_coords * 3                                                   # graph_transformer.py:53
+        in_edge_nf = 3 * use_intrinsic_coords + use_distances + 1 * (not use_intrinsic_coords) * (not use_distances)     # :54-58
+        self.node_embedding = nn.Linear(in_node_nf, hidden_nf)
+        self.edge_embedding = nn.Linear(in_edge_nf, hidden_nf)
         self.node_decoder = nn.Linear(hidden_nf, 1 if conservative else 3)      # graph_transformer.py:62-65
         self.graphtransformer = GraphTransformerLucid(hidden_nf, n_layers, hidden_nf)
         self.max_batch = 4096
@@ -96,7 +100,8 @@ class GraphTransformer(nn.Module):
             if self._eng is not None:
                 self._eng.close()
             state = {k: v.detach() for k, v in self.state_dict().items()}
-            self._eng = ScoreEngine(state, device=dev, max_batch=self.max_batch)
+            self._eng = ScoreEngine(state, device=dev, max_batch=self.max_batch, use_intrinsic_coords=self.use_intrinsic_coords,
+                                    use_distances=self.use_distances, use_abs_coords=self.use_abs_coords)
             self._eng_key = key
         return self._eng
 
