@@ -188,6 +188,22 @@ int dff_pwd_max_dev(const float* x_dev, int n, int num_beads, int offset, float*
 int dff_pwd_hist_dev(const float* x_dev, int n, int num_beads, int offset, float resolution, const int* nbins_dev,
                      int ld_hist, uint32_t* hist_dev, void* stream);
 
+/* ---- the other structure metrics of the reference's analysis suite, on device-resident samples x_dev [n, num_beads, 3] (Angstrom)
+ *
+ * Contact maps (evaluate/evaluators.py:735-858, ContactEvaluator): counts_dev [N*N] += number of samples with |x_i - x_j| < cutoff
+ * (caller zeroes it; normalised count = counts / n, :800-802); mismatch_dev [n] (nullable, caller zeroes) += number of pairs
+ * j - i >= offset whose contact state differs from folded_dev [N*N] (0/1 bytes) -- the per-frame binary cross entropy of
+ * _eval_bce_dynamics (:829-858) is 100 * mismatch / n_pairs. */
+int dff_contacts_dev(const float* x_dev, int n, int num_beads, float cutoff, const unsigned char* folded_dev, int offset,
+                     uint32_t* counts_dev, uint32_t* mismatch_dev, void* stream);
+/* Two backbone torsions per structure (mdtraj.compute_dihedrals formula in fp32; evaluators_CGflowmatching.py:32-38) of the atom
+ * quadruples quads_dev [2][4], written to torsions_dev [n][2] (nullable) and binned into hist_dev [nbins_axis][nbins_axis]
+ * (nullable, caller zeroes) over np.linspace(-pi, pi, nbins_axis + 1) like get_prob's np.histogram2d (:41-51). */
+int dff_dihedrals_dev(const float* x_dev, int n, int num_beads, const int* quads_dev, int nbins_axis, float* torsions_dev,
+                      uint32_t* hist_dev, void* stream);
+/* Minimal RMSD to ref_dev [num_beads, 3] after optimal superposition (mdtraj.rmsd of evaluators.py:655-660; Kabsch in fp64). */
+int dff_rmsd_dev(const float* x_dev, int n, int num_beads, const float* ref_dev, float* rmsd_dev, void* stream);
+
 /* Test hook: after a dff_score_* call with batch <= samples-per-CTA-group, copies the first CTA's
  * activation stash (the per-layer intermediates kept for the backward pass) to host.
  * Returns the number of floats written (<= cap) or a negative error. */

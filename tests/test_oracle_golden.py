@@ -163,3 +163,32 @@ def test_edge_modes_oracle_matches_reference():
             f64, e64, _ = collapsed_ref.forward_backward(score_ref.to_dtype(p, torch.float64), c["x"].double(), c["t_norm"], **kw)
             assert rel_err(f64, c["forces"]) < 5e-5, (key, rel_err(f64, c["forces"]))
             assert rel_err(e64, c["energy"]) < 5e-5, (key, rel_err(e64, c["energy"]))
+
+
+def test_structure_metrics_oracle():
+    """Contacts: the oracle restatement equals the reference's own ContactEvaluator outputs on the golden structures
+    (tests/golden/struct_metrics.pt, made by oracle/make_golden_struct.py).  Torsions / RMSD go through mdtraj in the reference
+    (absent here: parity unpinned): the restatements are checked on known geometry and invariances instead."""
+    import numpy as np
+    from oracle import metrics_ref
+    g = load("struct_metrics.pt")
+    norm, bce = metrics_ref.contact_stats(g["x"], g["folded"], g["cutoff"], g["offset"])
+    assert torch.equal(norm, g["contact_norm"]) and float(bce.mean()) == g["contact_bce_mean"]
+    # torsions: trans / cis / +-90 degree quadruples in the IUPAC sign convention mdtraj uses
+    base = np.array([[1.0, 0.0, 0.0], [0.0, 0.0, 0.0], [0.0, 1.0, 0.0]], dtype=np.float32)
+    for ang in (180.0, 0.0, 90.0, -90.0, 37.0):
+        a = np.deg2rad(ang)
+        p3 = np.array([[np.cos(a), 1.0, -np.sin(a)]], dtype=np.float32)
+        quad = np.concatenate([base, p3])[None]
+        got = float(metrics_ref.torsions(quad, quads=((0, 1, 2, 3),))[0, 0])
+        assert abs(((got - a + np.pi) % (2 * np.pi)) - np.pi) < 1e-6, (ang, got)
+    prob = metrics_ref.dihedral_prob(g["torsions"].numpy())
+    assert prob.shape == (60, 60) and abs(prob.sum() - 1) < 1e-12 and np.array_equal(prob, g["dihedral_prob"].numpy())
+    # RMSD: invariant under rotation + translation of the sample, zero for the reference itself, equals plain RMSD when aligned
+    x, ref = g["x"][:64], g["folded"]
+    q = torch.linalg.qr(torch.randn(3, 3, dtype=torch.float64, generator=torch.Generator().manual_seed(1)))[0]
+    q = q * torch.sign(torch.linalg.det(q))
+    moved = (x.double() @ q.t() + torch.tensor([3.0, -2.0, 7.0], dtype=torch.float64)).float()
+    r0, r1 = metrics_ref.rmsd_kabsch(x, ref), metrics_ref.rmsd_kabsch(moved, ref)
+    assert rel_err(r1, r0) < 1e-5 and float(metrics_ref.rmsd_kabsch(ref[None], ref)[0]) < 1e-6
+    assert bool((r0 <= (x.double() - x.double().mean(1, keepdim=True) - (ref.double() - ref.double().mean(0))).pow(2).sum((1, 2)).div(10).sqrt() + 1e-9).all())

@@ -794,6 +794,41 @@ int dff_pwd_hist_dev(const float* x_dev, int n, int num_beads, int offset, float
     return DFF_OK;
 }
 
+int dff_contacts_dev(const float* x_dev, int n, int num_beads, float cutoff, const unsigned char* folded_dev, int offset,
+                     uint32_t* counts_dev, uint32_t* mismatch_dev, void* stream) {
+    if (!x_dev || !counts_dev) return fail(DFF_EINVAL, "NULL argument");
+    if (num_beads < 2 || num_beads > 104) return fail(DFF_EINVAL, "num_beads %d unsupported for the shared-memory contact counters (2..104)", num_beads);
+    if (mismatch_dev && !folded_dev) return fail(DFF_EINVAL, "mismatch counts need the folded contact map");
+    if (n <= 0) return DFF_OK;
+    const long long total = (long long)n * num_beads * num_beads;
+    const int grid = (int)std::min<long long>((total + 255) / 256, 148LL * 8);
+    dff_contacts_kernel<<<grid, 256, (size_t)num_beads * num_beads * sizeof(unsigned int), (cudaStream_t)stream>>>(
+        x_dev, n, num_beads, cutoff, folded_dev, offset, counts_dev, mismatch_dev);
+    CUDA_TRY(cudaGetLastError());
+    return DFF_OK;
+}
+
+int dff_dihedrals_dev(const float* x_dev, int n, int num_beads, const int* quads_dev, int nbins_axis, float* torsions_dev,
+                      uint32_t* hist_dev, void* stream) {
+    if (!x_dev || !quads_dev) return fail(DFF_EINVAL, "NULL argument");
+    if (num_beads < 4 || (hist_dev && nbins_axis < 1)) return fail(DFF_EINVAL, "need >= 4 beads and >= 1 bin per axis");
+    if (n <= 0) return DFF_OK;
+    const int grid = std::min((n + 255) / 256, 148 * 8);
+    dff_dihedral_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x_dev, n, num_beads, quads_dev, nbins_axis, torsions_dev, hist_dev);
+    CUDA_TRY(cudaGetLastError());
+    return DFF_OK;
+}
+
+int dff_rmsd_dev(const float* x_dev, int n, int num_beads, const float* ref_dev, float* rmsd_dev, void* stream) {
+    if (!x_dev || !ref_dev || !rmsd_dev) return fail(DFF_EINVAL, "NULL argument");
+    if (num_beads < 1) return fail(DFF_EINVAL, "num_beads must be positive");
+    if (n <= 0) return DFF_OK;
+    const int grid = (int)std::min<long long>(((long long)n * 32 + 255) / 256, 148LL * 8);
+    dff_rmsd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x_dev, n, num_beads, ref_dev, rmsd_dev);
+    CUDA_TRY(cudaGetLastError());
+    return DFF_OK;
+}
+
 int64_t dff_debug_read_stash(dff_model_t* m, float* out_host, int64_t cap) {
     if (!m || !out_host) return fail(DFF_EINVAL, "NULL argument");
     if (cudaSetDevice(m->device) != cudaSuccess) return fail(DFF_ECUDA, "cudaSetDevice failed");

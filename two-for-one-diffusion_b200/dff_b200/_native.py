@@ -58,6 +58,9 @@ SYMBOLS = {
     "dff_pwd_num_pairs": (C.c_int, [C.c_int, C.c_int]),
     "dff_pwd_max_dev": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "dff_pwd_hist_dev": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_float, _vp, C.c_int, _vp, _vp]),
+    "dff_contacts_dev": (C.c_int, [_vp, C.c_int, C.c_int, C.c_float, _vp, C.c_int, _vp, _vp, _vp]),
+    "dff_dihedrals_dev": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, _vp]),
+    "dff_rmsd_dev": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp]),
     "dff_debug_read_stash": (C.c_int64, [_vp, _vp, C.c_int64]),
     "dff_debug_tc_gemm": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     "dff_debug_stash_layout": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),

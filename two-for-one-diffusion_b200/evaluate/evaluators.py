@@ -1,6 +1,6 @@
-"""The batching helpers of the sampling path (reference evaluate/evaluators.py:874-901) plus the two pure
-distribution metrics used for distributional parity (:905-948) and the pairwise-distance evaluator (:202-287) on the GPU.
-The rest of the analysis suite (dihedrals, TICA, RMSD, plots) is out of scope."""
+"""The batching helpers of the sampling path (reference evaluate/evaluators.py:874-901), the pure distribution metrics (:905-948)
+and the structure evaluators on the GPU: pairwise distances (:202-287), dihedral free energy (:114-176), RMSD to the folded
+structure (:608-680) and contacts (:735-858).  Plots and the TICA evaluator (needs deeptime models) are out of scope."""
 import os
 import pickle
 
@@ -71,3 +71,105 @@ class PwdEvaluator:
             raise NotImplementedError("plotting is not part of the B200 path")
         x = all_mol if all_mol.is_cuda else all_mol.cuda()
         return pwd_js(x, self.gt_hist, self.gt_max, self.offset, self.resolution)
+
+
+# ---- the helper metrics of evaluators_CGflowmatching.py:20-65 (numpy on 60 x 60 histograms)
+K_BT_IN_KCAL_PER_MOL = 1.380650324e-23 * 300 * 6.02214076e23 / 1000 / 4.184
+
+
+def mse_CGFM(density1, density2):
+    with np.errstate(divide="ignore"):
+        u1 = K_BT_IN_KCAL_PER_MOL * np.log(density1)
+        u2 = K_BT_IN_KCAL_PER_MOL * np.log(density2)
+    u1 = np.where(np.isinf(u1), np.nan, u1)
+    u2 = np.where(np.isinf(u2), np.nan, u2)
+    return np.nansum(np.square(u1 - u2)) / np.sum(np.isfinite(u1 - u2))
+
+
+def kl_div(density1, density2):
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ratio = density2 / density1
+    ratio[density1 == 0] = 1
+    ratio[density2 == 0] = 1
+    return -np.nansum(density1 * np.log(ratio))
+
+
+def folded_ca_coordinates(pdb_path, mol_name=""):
+    """C-alpha coordinates [N, 3] in Angstrom of a folded structure (reference process_pdb, evaluators.py:861-871: CA atoms,
+    protein G sliced to residues 5..60); works on the full PDBs and on the shipped `*-0-c-alpha.pdb` files."""
+    from dff_b200.pdb import load_pdb
+    top, xyz = load_pdb(pdb_path)
+    idx = [i for i, a in enumerate(top.atoms) if a.name == "CA"]
+    if mol_name.upper() == "PROTEIN_G" and len(idx) > 56:
+        idx = idx[5:61]
+    return torch.from_numpy(xyz[idx])
+
+
+class DihedralEnergiesEvaluator:
+    """Ramachandran free-energy evaluator (reference evaluators.py:114-176) against a saved reference histogram
+    (`saved_dih_probs_ala2_*.pickle`, a [60, 60] probability table).  Torsions and their 2-D histogram come from the GPU."""
+
+    def __init__(self, val_data=None, topology=None, plots_folder=None, n_bins=61, saved_ref="./saved_references/saved_dih_probs_ala2_testset.pickle"):
+        self.n_bins = n_bins
+        if not os.path.exists(saved_ref):
+            raise FileNotFoundError(f"{saved_ref}: a saved dihedral reference is required")
+        with open(saved_ref, "rb") as f:
+            self.gt_probs = pickle.load(f)
+
+    def eval(self, all_mol, plot_freeE=False, milestone=0, plot_title="Ramachandran plot", save_plot=True):
+        from dff_b200.metrics import torsions
+        if plot_freeE:
+            raise NotImplementedError("plotting is not part of the B200 path")
+        x = all_mol if all_mol.is_cuda else all_mol.cuda()
+        _, probs = torsions(x, n_bins=self.n_bins)
+        return mse_CGFM(probs, self.gt_probs), js_divergence(probs, self.gt_probs), kl_div(probs, self.gt_probs), kl_div(self.gt_probs, probs)
+
+
+class RmsdEvaluator:
+    """RMSD-to-folded free-energy profile (reference evaluators.py:608-680); `folded` = C-alpha pdb of the folded structure."""
+    cutoff_dict_ref = {"chignolin": 10, "trp_cage": 12, "bba": 14, "villin": 14, "protein_g": 20}
+
+    def __init__(self, mol_name, folded_pdb, eval_folder=None):
+        self.mol_name, self.plots_folder = mol_name, eval_folder
+        self.folded = folded_ca_coordinates(folded_pdb, mol_name)
+        self.plot_dict = {}
+        self.cutoff_ref, self.nbins_ref = self.cutoff_dict_ref.get(mol_name.lower()), 100
+
+    def eval(self, method, xyz, nbins, cutoff=None, save_dynamics=False):
+        from dff_b200.metrics import rmsd_to_reference
+        self.plot_dict[method] = {}
+        valid = torch.isfinite(xyz).all(-1).all(-1)
+        rmsd = np.full(len(xyz), np.nan)
+        xv = xyz[valid]
+        rmsd[valid.cpu().numpy()] = rmsd_to_reference(xv if xv.is_cuda else xv.cuda(), self.folded).double().cpu().numpy()
+        if save_dynamics:
+            self.plot_dict[method]["rmsd"] = rmsd
+        if cutoff is None:
+            cutoff = rmsd[~np.isnan(rmsd)].max()
+        h, edges = np.histogram(rmsd, bins=nbins, range=[0, cutoff], density=True)
+        self.plot_dict[method]["bin_mids"] = (edges[:-1] + edges[1:]) / 2.0
+        with np.errstate(divide="ignore"):
+            self.plot_dict[method]["energies"] = -np.log(h)
+        return self.plot_dict[method]
+
+
+class ContactEvaluator:
+    """Contact maps against the folded structure (reference evaluators.py:735-858); plots are out of scope, the numbers are kept:
+    normalised contact counts and the per-frame binary cross entropy to the folded contacts."""
+
+    def __init__(self, mol_name, folded_pdb, eval_folder=None, contact_cutoff=10):
+        self.mol_name, self.contact_cutoff, self.plots_folder = mol_name, contact_cutoff, eval_folder
+        self.folded = folded_ca_coordinates(folded_pdb, mol_name)
+        self.pwd_folded = torch.norm(self.folded[:, None, :] - self.folded[None, :, :], dim=-1)
+        self.contacts_folded = self.pwd_folded < self.contact_cutoff
+
+    def contact_normcount(self, xyz_sampled):
+        from dff_b200.metrics import contact_stats
+        x = xyz_sampled if xyz_sampled.is_cuda else xyz_sampled.cuda()
+        return contact_stats(x, self.folded, self.contact_cutoff)[0]
+
+    def bce_dynamics(self, xyz_sampled):
+        """per-frame BCE [n]; the reference's _eval_bce_dynamics returns its mean."""
+        from dff_b200.metrics import contact_stats
+        x = xyz_sampled if xyz_sampled.is_cuda else xyz_sampled.cuda()
+        return contact_stats(x, self.folded, self.contact_cutoff)[1]
