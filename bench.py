@@ -494,7 +494,7 @@ def main():
         if "c3" in extras:
             out["iid_samples_per_s"] = extras["c3"]["iid_samples_per_s"]
     if world == 1 and not a.no_cpu_baseline and not a.headline_only:
-        done, el, threads = oracle_rate(w, "cpu", seconds=15.0, max_steps=40, warm=2)
+        done, el, threads = oracle_rate(w, "cpu", seconds=15.0, max_steps=400, warm=2)
         out["cpu_baseline"] = {"value": done * B / el, "unit": unit, "cores": threads, "kind": "port",
                                "sample": f"{done} full-batch MD steps (B={B}) of the oracle port of the reference PyTorch CPU path, ~{el:.0f} s"}
         try:

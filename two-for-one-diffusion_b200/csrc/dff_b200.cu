@@ -41,6 +41,21 @@ int fail(int code, const char* fmt, ...) {
             return fail(DFF_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
+// Makes `device` current for the scope of an ABI call and restores the caller's device afterwards.
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
+        if (prev != device) ok = cudaSetDevice(device) == cudaSuccess;
+        else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define DEVICE_SCOPE(dev)                                                          \
+    DeviceGuard dg_(dev);                                                          \
+    if (!dg_.ok) return fail(DFF_ECUDA, "cudaSetDevice(%d) failed: %s", dev, cudaGetErrorString(cudaGetLastError()))
+
 struct SegHost {
     size_t offset;      // floats into the packed buffer
     uint32_t slice_bytes, n_slices;
@@ -172,7 +187,7 @@ int launch_tc(dff_model* m, int PN, int HP, int R, int ATT, const ModelDev& M, c
 int launch(dff_model* m, StepArgs& A, cudaStream_t stream) {
     if (A.B <= 0) return DFF_OK;
     if (A.B > m->max_batch) return fail(DFF_EINVAL, "batch %d exceeds max_batch %d given to dff_model_create", A.B, m->max_batch);
-    CUDA_TRY(cudaSetDevice(m->device));
+    DEVICE_SCOPE(m->device);
     const int N = m->N;
     const int s64 = 64 / N, s32 = 32 / N;
     enum { WIDE, TALL, DUO, TC } cfg;
@@ -310,7 +325,7 @@ int dff_model_create_v2(dff_model_t** out, int device, int num_beads, int hidden
     int ndev = dff_device_count();
     if (ndev <= 0) return fail(DFF_ENODEV, "no CUDA device visible: this library has no CPU fallback");
     if (device < 0 || device >= ndev) return fail(DFF_EINVAL, "device %d out of range (%d visible)", device, ndev);
-    CUDA_TRY(cudaSetDevice(device));
+    DEVICE_SCOPE(device);
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10)
@@ -619,7 +634,7 @@ int dff_model_create_v2(dff_model_t** out, int device, int num_beads, int hidden
 
 void dff_model_destroy(dff_model_t* m) {
     if (!m) return;
-    cudaSetDevice(m->device);
+    DeviceGuard dg_(m->device);
     if (m->d_weights) cudaFree(m->d_weights);
     for (auto p : m->d_segs) if (p) cudaFree(p);
     if (m->d_scratch) cudaFree(m->d_scratch);
@@ -658,7 +673,7 @@ int dff_score_dev(dff_model_t* m, const float* x_dev, float t_norm, int batch, f
 int dff_score_host(dff_model_t* m, const float* x_host, float t_norm, int batch, float* eps_out_host,
                    float* energy_out_host) {
     if (!m || !x_host) return fail(DFF_EINVAL, "NULL model or x");
-    CUDA_TRY(cudaSetDevice(m->device));
+    DEVICE_SCOPE(m->device);
     const size_t n = (size_t)batch * m->N;
     int rc;
     if ((rc = ensure_io(m, 0, n * 3)) || (rc = ensure_io(m, 1, n * 3)) || (rc = ensure_io(m, 2, n))) return rc;
@@ -710,7 +725,7 @@ int dff_langevin_steps_dev(dff_model_t* m, float* x_dev, float* v_dev, int batch
 int dff_ddpm_sample_host(dff_model_t* m, float* x_host, int batch, int T, const float* const* sched_host, uint64_t seed,
                          uint32_t* flags_host) {
     if (!m || !x_host || !sched_host) return fail(DFF_EINVAL, "NULL argument");
-    CUDA_TRY(cudaSetDevice(m->device));
+    DEVICE_SCOPE(m->device);
     const size_t n3 = (size_t)batch * m->N * 3;
     int rc;
     if ((rc = ensure_io(m, 0, n3))) return rc;
@@ -738,7 +753,7 @@ int dff_langevin_run_host(dff_model_t* m, float* x_host, float* v_host, int batc
                           const float* mass_host, uint64_t seed, int save_interval, float* frames_host, float* ke_host,
                           uint32_t* flags_host) {
     if (!m || !x_host || !p) return fail(DFF_EINVAL, "NULL argument");
-    CUDA_TRY(cudaSetDevice(m->device));
+    DEVICE_SCOPE(m->device);
     const size_t n3 = (size_t)batch * m->N * 3;
     const size_t nf = save_interval > 0 ? (size_t)(n_steps / save_interval) : 0;
     int rc;
@@ -831,7 +846,7 @@ int dff_rmsd_dev(const float* x_dev, int n, int num_beads, const float* ref_dev,
 
 int64_t dff_debug_read_stash(dff_model_t* m, float* out_host, int64_t cap) {
     if (!m || !out_host) return fail(DFF_EINVAL, "NULL argument");
-    if (cudaSetDevice(m->device) != cudaSuccess) return fail(DFF_ECUDA, "cudaSetDevice failed");
+    DEVICE_SCOPE(m->device);
     const int64_t n = std::min<int64_t>(cap, m->scratch_per_cta);
     if (cudaDeviceSynchronize() != cudaSuccess) return fail(DFF_ECUDA, "sync failed: %s", cudaGetErrorString(cudaGetLastError()));
     if (cudaMemcpy(out_host, m->d_scratch, n * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess)
