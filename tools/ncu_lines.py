@@ -21,7 +21,7 @@ for (f, l), (s, n, src) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
 
 # coarse attribution by source region of dff_kernel.cuh (function boundaries found by scanning the file)
 import os, re
-src = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "two-for-one-diffusion_b200", "csrc", "dff_kernel.cuh")
+src = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "two-for-one-diffusion_b200", "csrc", "dff_kernel_tc.cuh")
 if os.path.exists(src) and "--regions" in sys.argv:
     marks = []
     for i, line in enumerate(open(src), 1):
@@ -31,7 +31,7 @@ if os.path.exists(src) and "--regions" in sys.argv:
             if name: marks.append((i, name[0]))
     reg = collections.OrderedDict()
     for (f, l), (s, n, _) in agg.items():
-        if f != "dff_kernel.cuh":
+        if f != "dff_kernel_tc.cuh":
             key = f
         else:
             key = "?"
