@@ -361,3 +361,22 @@ def test_mirror_module_every_mode_and_sampling():
     xd = xc.cuda().contiguous()
     net.engine(xd.shape[0]).ddpm_steps(xd, 400, 2, 1000, [sched[k].cuda().contiguous() for k in SCHED_KEYS], noise=noise.cuda().contiguous())
     assert rel_err(xd, ref) < 2e-4
+
+
+@pytest.mark.parametrize("N,H,L,intr,dist,absc", [(12, 128, 3, False, True, True), (10, 64, 5, True, False, False), (7, 96, 4, True, True, True)])
+def test_job_tables_longer_than_the_shared_memory_cache(N, H, L, intr, dist, absc):
+    """Deep / absolute-coordinate nets need more than the 200 job-table entries cached in shared memory (216-260 here): the entries past
+    the cache are read from global memory by the TMA producer and the MMA issuer.  Forces vs the fp64 oracle."""
+    from dff_b200 import ScoreEngine
+    from oracle import collapsed_ref, score_ref
+    from oracle.weights import synthetic_net_params
+    in_edge = 3 * intr + dist + (not intr) * (not dist)
+    p = synthetic_net_params(N, H, L, seed=500 + N, in_edge=in_edge, in_node_extra=3 if absc else 0)
+    kw = dict(use_intrinsic_coords=intr, use_distances=dist, use_abs_coords=absc)
+    x = 0.8 * torch.randn(9, N, 3, generator=torch.Generator().manual_seed(N))
+    x = x - x.mean(1, keepdim=True)
+    eng = ScoreEngine(p, device="cuda:0", max_batch=16, **kw)
+    eps, en = eng.score(x.cuda(), 0.25, want_energy=True)
+    assert eng.last_config == "tc"
+    f64, e64, _ = collapsed_ref.forward_backward(score_ref.to_dtype(p, torch.float64), x.double(), 0.25, **kw)
+    assert rel_err(eps, f64) < FORCE_RTOL and rel_err(en, e64) < FORCE_RTOL, (rel_err(eps, f64), rel_err(en, e64))
