@@ -118,4 +118,9 @@ def test_evaluator_mirrors_on_gpu_samples(tmp_path):
     ce = ContactEvaluator("chignolin", pdb)
     norm, bce = ce.contact_normcount(xc), ce.bce_dynamics(xc)
     assert norm.shape == (10, 10) and float(norm.diagonal().min()) == 1.0 and bce.shape == (2048,)
+    # the combined Evaluator the reference's main_eval drives (dihedral JS for ala2) writes results-{milestone}.json
+    from evaluate.evaluators import Evaluator
+    import json
+    res = Evaluator(mol_name="alanine_dipeptide", eval_folder=str(tmp_path), saved_dihedral_ref=str(ref)).eval(xs, "best")
+    assert abs(res["Dihedral JS"] - js) < 1e-12 and json.load(open(tmp_path / "results-best.json")) == res
     print(f"[chignolin] mean RMSD-to-folded profile minimum at {out['bin_mids'][np.argmin(out['energies'])]:.2f} A, contact BCE {float(bce.mean()):.2f}")

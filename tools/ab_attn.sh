@@ -7,4 +7,4 @@ for att in "$@"; do
   for w in c2 c3 c4 c5; do timeout 300 python bench.py --workload $w --steps 3 --headline-only 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('   ', d['config']['workload'][:18], round(d['md_steps_per_s'],1), 'steps/s', round(d['roofline']['achieved'],2), 'TF/s')"; done
 done
 export DFF_ATTN=mma
-bash tools/tc_prof2.sh
+bash tools/tc_prof.sh

@@ -173,3 +173,38 @@ class ContactEvaluator:
         from dff_b200.metrics import contact_stats
         x = xyz_sampled if xyz_sampled.is_cuda else xyz_sampled.cuda()
         return contact_stats(x, self.folded, self.contact_cutoff)[1]
+
+
+class Evaluator:
+    """The evaluator `main_eval.py` / the trainer drive (reference evaluators.py:28-111): dihedral free energy for alanine dipeptide,
+    pairwise distances for the fast folders; results printed and written to `{eval_folder}/results-{milestone}.json`.  Both metrics
+    need their saved reference (`saved_dih_probs_*.pickle`, `saved_pwd_*.pickle`: building them from raw MD data is out of scope);
+    the TICA metric of the reference (deeptime models) is not computed."""
+
+    def __init__(self, ref_data=None, topology=None, mol_name="alanine", eval_folder=None, folded_pdb_folder="./datasets/folded_pdbs",
+                 data_folder="./data", evalsetname="", saved_dihedral_ref=None, saved_pwd_ref=None):
+        self.eval_folder, self.mol_name = eval_folder, mol_name
+        self.dihedral_evaluator = self.pwd_evaluator = None
+        if "alanine" in mol_name:
+            kw = {} if saved_dihedral_ref is None else {"saved_ref": saved_dihedral_ref}
+            self.dihedral_evaluator = DihedralEnergiesEvaluator(None, topology, eval_folder, **kw)
+        if "protein_g" != mol_name.lower() and (saved_pwd_ref is not None or "alanine" not in mol_name):
+            self.pwd_evaluator = PwdEvaluator(None, eval_folder, mol_name, offset=3, saved_ref=saved_pwd_ref or "none",
+                                              evalset=evalsetname or "testset")
+
+    def eval(self, sampled_mol, milestone, save_plots=False):
+        import json
+        res = {}
+        if self.dihedral_evaluator is not None:
+            print(f"Dihedral analysis {milestone}")
+            res["Dihedral JS"] = float(self.dihedral_evaluator.eval(sampled_mol, False, milestone)[1])
+        if self.pwd_evaluator is not None:
+            print(f"PWD Analysis {milestone}")
+            res["PWD JS"] = float(self.pwd_evaluator.eval(sampled_mol))
+        for key in res:
+            print(key + f": {res[key]:.4f}")
+        if self.eval_folder is not None:
+            with open(os.path.join(self.eval_folder, f"results-{milestone}.json"), "w") as f:
+                json.dump(res, f)
+        print("Evaluation done \n")
+        return res
