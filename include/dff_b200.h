@@ -123,6 +123,11 @@ double dff_model_flops_per_sample(const dff_model_t* m);
  *   energy_out_dev [B,N]    per-bead energies (return_energy=True, :109-110) */
 int dff_score_dev(dff_model_t* m, const float* x_dev, float t_norm, int batch,
                   float* eps_out_dev, float* energy_out_dev, void* stream);
+/* Same with one noise level PER SAMPLE: t_norm_dev [B] (device).  GraphTransformer.forward embeds t per sample
+ * (graph_transformer.py:91 `t.reshape(-1,1,1).repeat(1,N,1)`); the samplers always pass a uniform t, p_losses-style evaluation
+ * (models/ddpm.py:296-312) does not. */
+int dff_score_dev_t(dff_model_t* m, const float* x_dev, const float* t_norm_dev, int batch,
+                    float* eps_out_dev, float* energy_out_dev, void* stream);
 int dff_score_host(dff_model_t* m, const float* x_host, float t_norm, int batch,
                    float* eps_out_host, float* energy_out_host);
 

@@ -186,24 +186,53 @@ def test_langevin_distribution_matches_reference_run(rng):
     assert sampler_ref.js_divergence(h.numpy(), r["hist"].numpy()) < 5e-3, rng
 
 
-def test_forward_refuses_non_uniform_t_and_foreign_h():
-    """the kernel evaluates one noise level per call; a per-sample t or a non-identity h must raise, not silently
-    take t[0] / ignore h (reference: graph_transformer.py:91, 99-103)."""
+def test_forward_per_sample_t_and_foreign_h():
+    """the reference embeds t per sample (graph_transformer.py:91).  A non-uniform t now runs through the per-sample
+    entry point (dff_score_dev_t) and must match the reference restatement; a non-identity h or a wrong-sized t raises instead of
+    silently computing something else."""
     from dff_b200 import DffError
+    from oracle import score_ref
     ddpm = _ddpm("chignolin")
     x = load("score_chignolin.pt")["cases"][0]["x"].cuda()
     B = x.shape[0]
     ok = ddpm.model(x, ddpm.h, torch.full((B, 1, 1), 0.02, device="cuda"))
     assert ok.shape == x.shape
-    t_bad = torch.full((B,), 0.02, device="cuda"); t_bad[-1] = 0.5
-    with pytest.raises(DffError, match="same t"):
-        ddpm.model(x, ddpm.h, t_bad)
+    t_mixed = torch.tensor([0.02, 0.5, 0.005, 0.999, 0.0, 0.3][:B], device="cuda")
+    f = ddpm.model(x, ddpm.h, t_mixed)
+    e = ddpm.model(x, ddpm.h, t_mixed.reshape(-1, 1, 1), return_energy=True)
+    p = net_params("chignolin")
+    f_ref = score_ref.score_forward(p, x.cpu(), t_mixed.cpu())
+    e_ref = score_ref.score_forward(p, x.cpu(), t_mixed.cpu(), return_energy=True)
+    assert rel_err(f, f_ref) < FORCE_RTOL and rel_err(e, e_ref) < FORCE_RTOL, (rel_err(f, f_ref), rel_err(e, e_ref))
+    for b in range(B):          # and row b equals a uniform-t evaluation at t_b (per sample, against the reference's worst-case scale)
+        fb = ddpm.model(x, ddpm.h, torch.full((B,), float(t_mixed[b]), device="cuda"))
+        assert torch.equal(fb[b], f[b])
     with pytest.raises(DffError, match="entries"):
         ddpm.model(x, ddpm.h, torch.full((B + 1,), 0.02, device="cuda"))
     with pytest.raises(DffError, match="identity"):
         ddpm.model(x, torch.ones(10, 10), torch.full((B,), 0.02, device="cuda"))
     with pytest.raises(DffError):
         ddpm.model(x, torch.eye(9), torch.full((B,), 0.02, device="cuda"))
+
+
+def test_full_1000_step_sample_matches_reference():
+    """The reference's complete GaussianDiffusion.sample(batch_size=2) for ala2 (tests/golden/ddpm_full_ala2.pt: its CPU RNG state and
+    its output): the same draws (x_T, then one randn_like per step, in order) fed to the fused kernel, all 1000 steps in ONE launch."""
+    g = load("ddpm_full_ala2.pt")
+    ddpm = _ddpm("ala2_fold1")
+    gen_state = torch.get_rng_state()
+    torch.set_rng_state(g["rng_state"])
+    x = torch.randn(2, 5, 3)
+    x = x - x.mean(1, keepdim=True)
+    noise = torch.stack([torch.randn_like(x) for _ in range(1000)])
+    torch.set_rng_state(gen_state)
+    xd = x.cuda().contiguous()
+    eng = ddpm.model.engine(2)
+    l0 = eng.launches
+    eng.ddpm_steps(xd, 999, 1000, 1000, ddpm._sched_ptrs(), noise=noise.cuda().contiguous())
+    assert eng.launches == l0 + 1 and eng.read_flags() == 0
+    out = xd.cpu() * g["meta"]["std"]
+    assert rel_err(out, g["sample"]) < 1e-3, rel_err(out, g["sample"])
 
 
 def test_simulate_beyond_length_returns_only_real_frames():

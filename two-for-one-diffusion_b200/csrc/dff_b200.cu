@@ -670,6 +670,16 @@ int dff_score_dev(dff_model_t* m, const float* x_dev, float t_norm, int batch, f
     return launch(m, A, (cudaStream_t)stream);
 }
 
+int dff_score_dev_t(dff_model_t* m, const float* x_dev, const float* t_norm_dev, int batch, float* eps_out_dev,
+                    float* energy_out_dev, void* stream) {
+    if (!m || !x_dev || !t_norm_dev) return fail(DFF_EINVAL, "NULL model, x or t");
+    if (!m->conservative && energy_out_dev) return fail(DFF_EINVAL, "a non-conservative network has no energy output (graph_transformer.py:107-113)");
+    StepArgs A{};
+    A.mode = MODE_SCORE; A.B = batch; A.n_steps = 1; A.need_backward = m->conservative && eps_out_dev != nullptr;
+    A.x = const_cast<float*>(x_dev); A.eps_out = eps_out_dev; A.energy_out = energy_out_dev; A.t_norm = 0.f; A.t_rows = t_norm_dev;
+    return launch(m, A, (cudaStream_t)stream);
+}
+
 int dff_score_host(dff_model_t* m, const float* x_host, float t_norm, int batch, float* eps_out_host,
                    float* energy_out_host) {
     if (!m || !x_host) return fail(DFF_EINVAL, "NULL model or x");

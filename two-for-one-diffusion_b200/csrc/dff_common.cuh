@@ -83,6 +83,7 @@ struct StepArgs {
     float* frames; float* ke;
     unsigned long long seed, offset;
     uint32_t* flags;
+    const float* t_rows;            // MODE_SCORE only: per-sample t / T [B] (graph_transformer.py:91 embeds t per sample); NULL: t_norm for all
 };
 
 // ---------------------------------------------------------------- PTX helpers

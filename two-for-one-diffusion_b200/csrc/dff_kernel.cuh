@@ -646,7 +646,7 @@ __device__ __forceinline__ void softmax_backward_rows(float* sDS, const float* s
 
 // ------------------------------------------------------------------ forward pass (energy) for one group of samples
 template <class C>
-__device__ void forward_pass(const ModelDev& M, Ctx& c, float t_norm) {
+__device__ void forward_pass(const ModelDev& M, Ctx& c, float t_norm, const float* __restrict__ t_rows) {
     constexpr int HP = C::kHP, R = C::kR, HC = C::kHC;
     const int tid = threadIdx.x;
     const int N = M.N, NP = M.NP, H = M.H;
@@ -655,7 +655,7 @@ __device__ void forward_pass(const ModelDev& M, Ctx& c, float t_norm) {
     for (int idx = tid; idx < R * HP; idx += kThreads) {
         const int r = idx / HP, d = idx - r * HP;
         float v = 0.f;
-        if (r < c.rows_act && d < H) v = __ldg(M.emb + (r % N) * H + d) + t_norm * __ldg(M.embt + d);
+        if (r < c.rows_act && d < H) v = __ldg(M.emb + (r % N) * H + d) + (t_rows != nullptr ? __ldg(t_rows + r / N) : t_norm) * __ldg(M.embt + d);
         c.sN[r * C::LDH + d] = v;
     }
     __syncthreads();
@@ -967,7 +967,7 @@ dff_fused_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ Ste
             const int it = A.t_start - step;
             const float t_norm = (A.mode == MODE_DDPM) ? (float)it / (float)A.T : A.t_norm;
 
-            forward_pass<C>(M, c, t_norm);
+            forward_pass<C>(M, c, t_norm, (A.mode == MODE_SCORE && A.t_rows != nullptr) ? A.t_rows + s0 : nullptr);
             if (A.energy_out != nullptr) {   // node_decoder (graph_transformer.py:106)
                 const int lane = tid & 31, warp = tid >> 5;
                 for (int r = warp; r < c.rows_act; r += kWarps) {

@@ -1340,7 +1340,7 @@ constexpr int kLDF = 256 + 4;
 
 // ------------------------------------------------------------------ forward pass (compute warps)
 template <class C>
-__device__ void forward_pass_tc(const ModelDev& M, Ctx2& c, float t_norm) {
+__device__ void forward_pass_tc(const ModelDev& M, Ctx2& c, float t_norm, const float* __restrict__ t_rows) {
     constexpr int R = C::kR;
     const int tid = threadIdx.x;
     const int N = M.N, NP = M.NP, H = M.H;
@@ -1349,7 +1349,8 @@ __device__ void forward_pass_tc(const ModelDev& M, Ctx2& c, float t_norm) {
     // layer-0 node stream: W_n [onehot_i, t] + b_n   (graph_transformer.py:99-103)
     for (int idx = tid; idx < rows * C::kHP; idx += kCT) {
         const int r = idx / C::kHP, d = idx - r * C::kHP;
-        float v = (d < H) ? __ldg(M.emb + (r % N) * H + d) + t_norm * __ldg(M.embt + d) : 0.f;
+        const float tn = t_rows != nullptr ? __ldg(t_rows + r / N) : t_norm;          // per-sample noise level (score mode) or the shared one
+        float v = (d < H) ? __ldg(M.emb + (r % N) * H + d) + tn * __ldg(M.embt + d) : 0.f;
         if (M.abs_coords && d < H)        // node input [onehot_i, x_i, t] (graph_transformer.py:99-100)
             v += c.sX[r * 4] * __ldg(M.embx + d) + c.sX[r * 4 + 1] * __ldg(M.embx + H + d) + c.sX[r * 4 + 2] * __ldg(M.embx + 2 * H + d);
         c.sN[r * C::LDH + d] = v;
@@ -1916,7 +1917,7 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
                 const float t_norm = (A.mode == MODE_DDPM) ? (float)it / (float)A.T : A.t_norm;
 
                 c.mark(22);
-                forward_pass_tc<C>(M, c, t_norm);
+                forward_pass_tc<C>(M, c, t_norm, (A.mode == MODE_SCORE && A.t_rows != nullptr) ? A.t_rows + s0 : nullptr);
                 if (A.energy_out != nullptr) {   // node_decoder (graph_transformer.py:106)
                     const int lane = tid & 31;
                     for (int r = warp; r < c.rows_act; r += kCW) {

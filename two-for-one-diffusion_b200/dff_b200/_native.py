@@ -47,6 +47,7 @@ SYMBOLS = {
     "dff_model_last_config": (C.c_char_p, [_vp]),
     "dff_model_flops_per_sample": (C.c_double, [_vp]),
     "dff_score_dev": (C.c_int, [_vp, _vp, C.c_float, C.c_int, _vp, _vp, _vp]),
+    "dff_score_dev_t": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, _vp, _vp]),
     "dff_score_host": (C.c_int, [_vp, _vp, C.c_float, C.c_int, _vp, _vp]),
     "dff_ddpm_steps_dev": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp), _vp, C.c_uint64,
                                      C.c_uint64, _vp, _vp]),

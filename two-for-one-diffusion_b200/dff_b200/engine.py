@@ -104,14 +104,21 @@ class ScoreEngine:
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     # ---- == GraphTransformer.forward
-    def score(self, x: torch.Tensor, t_norm: float, want_forces=True, want_energy=False):
+    def score(self, x: torch.Tensor, t_norm, want_forces=True, want_energy=False):
+        """t_norm: a python float (one noise level for the batch) or a [B] float32 device tensor (one per sample)."""
         x = _dev_f32(x, self.device)
         B = x.shape[0]
         assert x.shape[1:] == (self.num_beads, 3), x.shape
         eps = torch.empty_like(x) if want_forces else None
         en = torch.empty(B, self.num_beads, device=self.device, dtype=torch.float32) if want_energy else None
         with torch.cuda.device(self.device):
-            nat.check(nat.lib().dff_score_dev(self._h, _ptr(x), float(t_norm), B, _ptr(eps), _ptr(en), self._stream()))
+            if torch.is_tensor(t_norm):
+                t = _dev_f32(t_norm.reshape(-1), self.device)
+                if t.numel() != B:
+                    raise nat.DffError(f"t has {t.numel()} entries for a batch of {B}")
+                nat.check(nat.lib().dff_score_dev_t(self._h, _ptr(x), _ptr(t), B, _ptr(eps), _ptr(en), self._stream()))
+            else:
+                nat.check(nat.lib().dff_score_dev(self._h, _ptr(x), float(t_norm), B, _ptr(eps), _ptr(en), self._stream()))
         return eps, en
 
     # ---- == GaussianDiffusion.p_sample_loop slice (in place on x)

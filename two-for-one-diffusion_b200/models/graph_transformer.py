@@ -106,19 +106,17 @@ class GraphTransformer(nn.Module):
         return self._eng
 
     @staticmethod
-    def _shared_t(t) -> float:
-        """The kernel evaluates one noise level per call (every caller on the sampling path passes a uniform t:
-        ddpm.py:240-247, langevin.py:77); the reference embeds t per sample (graph_transformer.py:91), so a
-        non-uniform t would silently give different numbers -- refuse it instead."""
-        if torch.is_tensor(t):
-            flat = t.reshape(-1)
-            if flat.numel() == 0:
-                raise DffError("t is empty")
-            if flat.numel() > 1 and not bool((flat == flat[0]).all()):
-                raise DffError("GraphTransformer.forward on B200 needs the same t for the whole batch "
-                               "(per-sample noise levels are a training-path feature: split the batch by t)")
+    def _t_arg(t, batch, device):
+        """One noise level for the batch (every caller on the sampling path: ddpm.py:240-247, langevin.py:77) -> python float;
+        per-sample noise levels (graph_transformer.py:91 embeds t per sample; p_losses-style evaluation) -> [B] device tensor."""
+        if not torch.is_tensor(t):
+            return float(t)
+        flat = t.reshape(-1)
+        if flat.numel() not in (1, batch):
+            raise DffError(f"t has {flat.numel()} entries for a batch of {batch}")
+        if flat.numel() == 1 or bool((flat == flat[0]).all()):
             return float(flat[0])
-        return float(t)
+        return flat.detach().to(device, torch.float32).contiguous()
 
     def _check_h(self, h):
         """`h` must be the bead one-hot matrix the node embedding was folded with (graph_transformer.py:99-103 with
@@ -135,14 +133,12 @@ class GraphTransformer(nn.Module):
             self._h_ok = key
 
     def forward(self, x, h, t, return_energy=False, alphas: Optional[torch.Tensor] = None):
-        """x [B,N,3]; h [N,N] bead one-hot (identity); t [B] / [B,1,1] = step/T shared by the batch.
+        """x [B,N,3]; h [N,N] bead one-hot (identity); t [B] / [B,1,1] = step/T (uniform or one value per sample).
         Returns forces (= -dE/dx, the epsilon prediction) [B,N,3], or energies [B,N,1] if return_energy.
         `alphas` is accepted and unused, exactly like the reference (graph_transformer.py:83)."""
         self._check_h(h)
-        t_shared = self._shared_t(t)
-        if torch.is_tensor(t) and t.reshape(-1).numel() not in (1, x.shape[0]):
-            raise DffError(f"t has {t.reshape(-1).numel()} entries for a batch of {x.shape[0]}")
         eng = self.engine(x.shape[0])
+        t_shared = self._t_arg(t, x.shape[0], eng.device)
         xin = x.detach().to(eng.device, torch.float32).contiguous()
         if not self.conservative:       # the decoder output is the prediction; return_energy is ignored (:107-113)
             return eng.score(xin, t_shared, want_forces=True, want_energy=False)[0]
