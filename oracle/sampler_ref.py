@@ -174,6 +174,19 @@ def langevin_simulate(score: Callable, c: dict, x0: torch.Tensor, masses, fricti
     return coords, ke, x, v
 
 
+def p_losses(score: Callable, sched: Dict[str, torch.Tensor], x_start: torch.Tensor, t: torch.Tensor, noise: torch.Tensor,
+             T: int = 1000) -> torch.Tensor:
+    """GaussianDiffusion.p_losses (ddpm.py:289-315) with the q_sample of :265-274, l2 loss, pred_noise objective.
+    `score(x, t_norm[B])` evaluates the network with one noise level per sample."""
+    noise = center_zero(noise)
+    sa = sched["sqrt_alphas_cumprod"][t].reshape(-1, 1, 1)
+    so = sched["sqrt_one_minus_alphas_cumprod"][t].reshape(-1, 1, 1)
+    x = center_zero(sa * x_start + so * noise)
+    out = center_zero(score(x, 1.0 * t / T))
+    loss = torch.nn.functional.mse_loss(out, noise, reduction="none")
+    return loss.reshape(loss.shape[0], -1).mean(dim=1).mean()
+
+
 def num_to_groups(num: int, divisor: int):
     """evaluate/evaluators.py:891-901."""
     arr = [divisor] * (num // divisor)

@@ -291,3 +291,23 @@ def test_langevin_npy_export_log_and_restart(tmp_path, rng):
     b.load_state_dict(torch.load(tmp_path / "restart.pt", weights_only=False))
     tail = b.simulate(sub_interval=30)
     assert b.t == 60 and np.array_equal(tail, coords[:, 3:])
+
+
+@pytest.mark.parametrize("mol", ["chignolin", "ala2_fold1", "trp_cage"])
+def test_p_losses_matches_reference(mol):
+    """Loss evaluation (the forward half of the training path, trainer.eval_loss): GaussianDiffusion.p_losses with per-sample noise
+    levels against the reference's values (tests/golden/p_losses.pt); forward() draws its own t and runs the KL check; training mode
+    (parameter gradients) is refused."""
+    from dff_b200 import DffError
+    g = load("p_losses.pt")[mol]
+    ddpm = _ddpm(mol)
+    loss = ddpm.p_losses(g["x_start"].cuda(), g["t"].cuda(), noise=g["noise"].cuda())
+    assert abs(float(loss) - float(g["loss"])) < 1e-4 * abs(float(g["loss"])), (float(loss), float(g["loss"]))
+    per = torch.stack([ddpm.p_losses(g["x_start"][b:b + 1].cuda(), g["t"][b:b + 1].cuda(), noise=g["noise"][b:b + 1].cuda()) for b in range(12)])
+    assert rel_err(per, g["per_sample"]) < 2e-4
+    torch.manual_seed(1)
+    val = ddpm(g["x_start"].cuda() * g["std"])                     # Angstrom in, random t, evaluation mode
+    assert val.ndim == 0 and 0.0 < float(val) < 10.0
+    ddpm.train()
+    with pytest.raises(DffError, match="second-order"):
+        ddpm(g["x_start"].cuda() * g["std"])

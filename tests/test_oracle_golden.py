@@ -192,3 +192,16 @@ def test_structure_metrics_oracle():
     r0, r1 = metrics_ref.rmsd_kabsch(x, ref), metrics_ref.rmsd_kabsch(moved, ref)
     assert rel_err(r1, r0) < 1e-5 and float(metrics_ref.rmsd_kabsch(ref[None], ref)[0]) < 1e-6
     assert bool((r0 <= (x.double() - x.double().mean(1, keepdim=True) - (ref.double() - ref.double().mean(0))).pow(2).sum((1, 2)).div(10).sqrt() + 1e-9).all())
+
+
+@pytest.mark.parametrize("mol", ("chignolin", "ala2_fold1", "trp_cage"))
+def test_p_losses_oracle_matches_reference(mol):
+    """The denoising loss with per-sample noise levels (GaussianDiffusion.p_losses, ddpm.py:289-315): the oracle restatement
+    against the reference's own values (tests/golden/p_losses.pt)."""
+    g = load("p_losses.pt")[mol]
+    p, sched = net_params(mol), schedule(mol)
+    score = lambda x, tn: score_ref.score_forward(p, x, tn)
+    loss = sampler_ref.p_losses(score, sched, g["x_start"], g["t"], g["noise"])
+    assert abs(float(loss) - float(g["loss"])) < 2e-6 * abs(float(g["loss"]))
+    per = torch.stack([sampler_ref.p_losses(score, sched, g["x_start"][b:b + 1], g["t"][b:b + 1], g["noise"][b:b + 1]) for b in range(12)])
+    assert rel_err(per, g["per_sample"]) < 1e-5

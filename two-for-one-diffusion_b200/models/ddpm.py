@@ -2,8 +2,8 @@
 
 `p_sample_loop` hands whole slices of the 1000-step reverse chain to ONE launch of the fused kernel
 (score forward+backward and the posterior update per step, coordinates resident on chip), instead of
-~300 ATen kernels and 3 host syncs per step.  The training half (q_sample / p_losses / forward,
-ddpm.py:265-337) is out of scope.
+~300 ATen kernels and 3 host syncs per step.  Of the training half (ddpm.py:265-337) the loss EVALUATION is provided
+(q_sample / p_losses / forward under no_grad, what trainer.eval_loss runs); parameter gradients are out of scope.
 """
 import warnings
 
@@ -134,5 +134,53 @@ class GaussianDiffusion(nn.Module):
     def sample(self, batch_size):
         return self.p_sample_loop((batch_size, self.num_atoms, self.dims)) * self.norm_factor
 
-    def forward(self, *a, **k):
-        raise DffError("training (p_losses / forward) is out of scope of the B200 sampling path")
+    # ---- loss evaluation (the forward half of the training path: what trainer.eval_loss runs under no_grad, trainer.py:222-235)
+    def q_mean_variance(self, x_start, t):
+        mean = extract(self.sqrt_alphas_cumprod, t, x_start.shape) * x_start
+        return mean, extract(1.0 - self.alphas_cumprod, t, x_start.shape), extract(self.log_one_minus_alphas_cumprod, t, x_start.shape)
+
+    @torch.no_grad()
+    def assert_normal_kl(self, x_start, t, eps=1e-4):
+        """KL(q(x_T | x_0) || N(0, I)) must vanish: enough diffusion steps (ddpm.py:173-193)."""
+        assert_center_zero(x_start)
+        mean1, _, logvar1 = self.q_mean_variance(x_start, t)
+        logvar1 = logvar1.squeeze()
+        kl = 0.5 * (-1.0 - logvar1 + torch.exp(logvar1) + (mean1 ** 2).sum(dim=(-2, -1)))
+        assert kl.abs().max().item() <= eps, f"Normal KL check at T failed, max value: {kl.abs().max().item()}"
+
+    def q_sample(self, x_start, t, noise=None):
+        noise = center_zero(torch.randn_like(x_start) if noise is None else noise)
+        return extract(self.sqrt_alphas_cumprod, t, x_start.shape) * x_start \
+            + extract(self.sqrt_one_minus_alphas_cumprod, t, x_start.shape) * noise
+
+    @property
+    def loss_fn(self):
+        if self.loss_type == "l1":
+            return F.l1_loss
+        if self.loss_type == "l2":
+            return F.mse_loss
+        raise ValueError(f"invalid loss type {self.loss_type}")
+
+    @torch.no_grad()
+    def p_losses(self, x_start, t, noise=None):
+        """The denoising loss at per-sample noise levels t [B] (ddpm.py:289-315).  The score network runs in the fused kernel with one t
+        per sample (dff_score_dev_t); VALUE only: parameter gradients need a second-order reverse pass of the kernel (the training
+        step, SURVEY.md 8f rank 4, is out of scope), so this is what `trainer.eval_loss` computes, not what `trainer.train` needs."""
+        noise = center_zero(torch.randn_like(x_start) if noise is None else noise)
+        x = center_zero(self.q_sample(x_start=x_start, t=t, noise=noise))
+        model_out = center_zero(self.model(x, self.h, 1.0 * t / self.num_timesteps, alphas=None))
+        loss = self.loss_fn(model_out, noise, reduction="none")
+        return loss.reshape(loss.shape[0], -1).mean(dim=1).mean()
+
+    def forward(self, mol, *args, t_diff_range=None, **kwargs):
+        """Loss of a batch of structures in Angstrom at random noise levels (ddpm.py:317-337); evaluation only."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.model.parameters()) and self.training:
+            raise DffError("GaussianDiffusion.forward in training mode needs parameter gradients (a second-order reverse pass of the "
+                           "fused kernel): out of scope.  Call it in eval mode / under torch.no_grad() for the loss value (trainer.eval_loss)")
+        mol = center_zero(mol) / self.norm_factor
+        assert_center_zero(mol)
+        b, n, d = mol.shape
+        assert n == self.num_atoms and d == self.dims, f"Molecule shape must be {(self.num_atoms, self.dims)}"
+        t = torch.multinomial(self.p2_loss_weight, b, replacement=True).long()
+        self.assert_normal_kl(x_start=mol, t=torch.full((b,), self.num_timesteps - 1, device=mol.device, dtype=torch.long))
+        return self.p_losses(mol, t, *args, **kwargs)
