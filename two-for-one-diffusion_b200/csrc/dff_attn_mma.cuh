@@ -235,7 +235,7 @@ __device__ __forceinline__ float dist2(const float* sX, int r, int rk) {
 // Forward phase 2: softmax over the keys of the row's sample, in place; p -> stash.  One warp per row, lane = key (and key + 32).
 // Distance channel: logit_uj += s alpha_u |x_u - x_j|^2  and  z_u = sum_j p_uj |x_u - x_j|^2 -> sZ[u * ldz]
 template <class C>
-__device__ __forceinline__ void attn_softmax_rows(float* sP, float* st_p, const float* sQKV, const float* sX, float* sZ, int ldz, bool dist, const AttnGeo& G) {
+__device__ __forceinline__ void attn_softmax_rows(float* sP, const float* sQKV, const float* sX, float* sZ, int ldz, bool dist, const AttnGeo& G) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rows = G.S_act * G.N;
     for (int r = warp; r < rows; r += kCW) {
@@ -255,8 +255,8 @@ __device__ __forceinline__ void attn_softmax_rows(float* sP, float* st_p, const 
         const float e0 = a0 ? expf(l0 - m) : 0.f, e1 = a1 ? expf(l1 - m) : 0.f;
         const float inv = 1.0f / warp_sum(e0 + e1);
         const float p0 = e0 * inv, p1 = e1 * inv;
-        if (lane < G.NP) { row[lane] = p0; st_p[(size_t)r * G.NP + lane] = p0; }
-        if (lane + 32 < G.NP) { row[lane + 32] = p1; st_p[(size_t)r * G.NP + lane + 32] = p1; }
+        if (lane < G.NP) row[lane] = p0;              // (the caller copies sP to the stash)
+        if (lane + 32 < G.NP) row[lane + 32] = p1;
         if (dist) {
             const float z = warp_sum(p0 * d0 + p1 * d1);
             if (lane == 0) sZ[r * ldz] = z;

@@ -101,7 +101,7 @@ void stash_geometry(int R, int N_pad, int H, long long* off, long long* layer_fl
     auto put = [&](int region, long long n) { off[region] = o; o += (n + 3) / 4 * 4; };
     put(ST_NIN, (long long)R * H);
     put(ST_STAT1, 2LL * R);
-    put(ST_QKV, 8LL * R * 192);
+    put(ST_QKV, 8LL * R * 196);          // rows keep the shared-memory stride (192 + 4 pad) so that a chunk moves as one bulk copy
     put(ST_P, 8LL * R * N_pad);
     put(ST_ATT, (long long)R * H);
     put(ST_G1, R);
@@ -165,11 +165,11 @@ int launch_tc(dff_model* m, int PN, int HP, int R, int ATT, const ModelDev& M, c
         for (int b = 0; b < grid; ++b) for (int i = 0; i < 16; ++i) s[i] += (double)h[(size_t)b * 16 + i] / grid;
         fprintf(stderr, "[tc profile] grid %d steps %d: compute total %.0f cyc; waits dq %.0f acc %.0f d1 %.0f slot %.0f | issuer total %.0f: post %.0f drain %.0f weights %.0f | producer empty-wait %.0f\n",
                 grid, A.n_steps, s[7], s[0], s[1], s[2], s[3], s[12], s[9], s[10], s[11], s[8]);
-        static const char* names[28] = {"f.init+ln", "dq_wait", "f.qkv_epi", "f.attn", "f.slot_post", "acc_wait", "f.acc_epi", "f.gate+post", "d1_wait", "f.d1copy",
+        static const char* names[32] = {"f.init+ln", "dq_wait", "f.qkv_epi", "f.attn", "f.slot_post", "acc_wait", "f.acc_epi", "f.gate+post", "d1_wait", "f.d1copy",
                                         "f.gelu", "b.gate2+post", "b.d1copy", "b.gelu'", "b.accepi+gate1+post", "b.reload_issue", "b.do_epi", "b.ds", "b.dq+post",
-                                        "b.dk+post", "b.dv+post", "b.acc+lnbwd", "integrator", "f.logits", "f.softmax", "b.dp_uw", "b.dx", "b.dk'"};
+                                        "b.dk+post", "b.dv+post", "b.acc+lnbwd", "integrator", "f.logits", "f.softmax", "b.dp_uw", "b.dx", "b.dk'", "fq.pre", "fq.dots", "fq.softmax", "fq.pv"};
         fprintf(stderr, "[tc phases, CTA 0, cycles per step]");
-        for (int i = 0; i < 28; ++i) fprintf(stderr, " %s %.0f |", names[i], (double)h[(size_t)grid * 16 + i] / A.n_steps);
+        for (int i = 0; i < 32; ++i) fprintf(stderr, " %s %.0f |", names[i], (double)h[(size_t)grid * 16 + i] / A.n_steps);
         fprintf(stderr, "\n");
     }
 #endif

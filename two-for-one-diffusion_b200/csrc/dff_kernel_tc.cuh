@@ -140,7 +140,7 @@ struct TcCfg {
 //   B_POST  ring of 8: compute -> issuer "operand ready" (post i arrives on slot i & 7; the compute warps can never be more than
 //           two posts ahead of the issuer: every slot_post first waits for the previous slot job)
 //   B_DRAIN 2: compute -> issuer "double-buffered accumulator b read back"
-enum { B_FULL = 0, B_EMPTY = 4, B_DQ = 8, B_ACC = 10, B_D1 = 11, B_SLOT = 12, B_POST = 16, B_DRAIN = 24, B_COUNT = 26 };      // room for 4 ring stages
+enum { B_FULL = 0, B_EMPTY = 4, B_DQ = 8, B_ACC = 10, B_D1 = 11, B_SLOT = 12, B_RELOAD = 13, B_POST = 16, B_DRAIN = 24, B_COUNT = 26 };      // room for 4 ring stages
 
 // ------------------------------------------------------------------ small PTX helpers
 __device__ __forceinline__ void csync() { asm volatile("bar.sync 1, %0;" ::"n"(kCT) : "memory"); }   // the compute warps
@@ -254,7 +254,7 @@ struct Ctx2 {
     float *nhat_hi, *nhat_lo, *slot_hi, *slot_lo;
     uint64_t* bars;
     uint32_t tmem;
-    uint32_t n_post, n_drain, n_acc, n_d1, n_slot;   // identical in every compute thread
+    uint32_t n_post, n_drain, n_acc, n_d1, n_slot, n_reload;   // identical in every compute thread
     bool slot_held;
     bool pairs;            // pair-local attention routines (groups with more rows than lane groups)
     bool quads;            // quad-local routines (N > 32: two keys per lane, one quad per warp)
@@ -538,6 +538,30 @@ __device__ __forceinline__ float group_max(float v) {
     for (int o = LPR / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
+// K independent reductions at once: the K shuffles of a butterfly step are issued back to back, so their latencies
+// overlap (K separate group_sum calls separated by branches run their 5-shuffle chains one after the other)
+template <int LPR, int K>
+__device__ __forceinline__ void group_sum_n(float (&v)[K]) {
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) {
+        float t[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) t[k] = __shfl_xor_sync(0xffffffffu, v[k], o);
+#pragma unroll
+        for (int k = 0; k < K; ++k) v[k] += t[k];
+    }
+}
+template <int LPR, int K>
+__device__ __forceinline__ void group_max_n(float (&v)[K]) {
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) {
+        float t[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) t[k] = __shfl_xor_sync(0xffffffffu, v[k], o);
+#pragma unroll
+        for (int k = 0; k < K; ++k) v[k] = fmaxf(v[k], t[k]);
+    }
+}
 // dots of one (or two) shared-memory rows a (a2) with the N rows b_j of the sample, for all j at once:
 // every lane takes the DPL columns it owns, forms the partial products for every key j and the partials are then
 // summed across the group by a transpose-reduce (LPR - 1 shuffles), after which lane j holds  a . b_j.
@@ -679,8 +703,8 @@ __device__ __forceinline__ void attn_forward_rows(Ctx2& c, const LayerDev& W, in
         group_dots<LPR, DPL, false>(c.sQKV + u * C::LDQ, nullptr, c.sQKV + r0 * C::LDQ + 64, C::LDQ, N, sub, dot, dot_unused);
         const float lg = act ? kAttnScale * dot : -INFINITY;
         const float m = group_max<LPR>(lg);
-        const float e = act ? expf(lg - m) : 0.f;
-        const float p = e / group_sum<LPR>(e);
+        const float e = expf(lg - m);                  // exp(-inf) = 0 for the inactive keys
+        const float p = e * __frcp_rn(group_sum<LPR>(e));
         if (valid && sub < NP) st_p[(size_t)u * NP + sub] = p;
         float acc[DPL];
 #pragma unroll
@@ -884,14 +908,13 @@ __device__ __forceinline__ void attn_forward_pairs(Ctx2& c, const LayerDev& W, i
         float pa[KPL], pb[KPL], sa = 0.f, sb = 0.f;
 #pragma unroll
         for (int kp = 0; kp < KPL; ++kp) {
-            const bool act = kp * LPR + sub < N;
-            pa[kp] = act ? expf(la[kp] - ma) : 0.f; pb[kp] = act ? expf(lb[kp] - mb) : 0.f;
+            pa[kp] = expf(la[kp] - ma); pb[kp] = expf(lb[kp] - mb);        // exp(-inf) = 0 for the inactive keys
             sa += pa[kp]; sb += pb[kp];
         }
-        sa = group_sum<LPR>(sa); sb = group_sum<LPR>(sb);
+        sa = __frcp_rn(group_sum<LPR>(sa)); sb = __frcp_rn(group_sum<LPR>(sb));
 #pragma unroll
         for (int kp = 0; kp < KPL; ++kp) {
-            pa[kp] = pa[kp] / sa; pb[kp] = pb[kp] / sb;
+            pa[kp] *= sa; pb[kp] *= sb;
             const int key = kp * LPR + sub;
             if (u.valid && key < NP) {
                 st_p[(size_t)ra * NP + key] = pa[kp];
@@ -1142,26 +1165,39 @@ __device__ __forceinline__ void attn_forward_quads(Ctx2& c, const LayerDev& W, i
         ax[e][0] = a4.x; ax[e][1] = a4.y; ax[e][2] = a4.z;
     }
     // rows of the quad (clamped for the padded tail); all four are read with one base pointer and stride LDQ
+    c.mark(28);
     const int rbase = u.r0 + min(u.i0, max(N - 4, 0));               // keep the 4 rows inside the sample: shift the window back
     const int shift = u.i0 - (rbase - u.r0);                          // rows [shift, 4) of the window are this quad's rows
     float d[4][2];
     lane_dots8<AM::KPL>(c.sQKV + rbase * C::LDQ, C::LDQ, c.sQKV + (u.r0 + min(sub, N - 1)) * C::LDQ + 64,
                c.sQKV + (u.r0 + min(LPR + sub, N - 1)) * C::LDQ + 64, d);
+    c.mark(29);
     const bool act0 = sub < N, act1 = LPR + sub < N;
-    float p[4][2];
+    // softmax of the four rows: branch-free (exp(-inf) = 0 masks the inactive keys) with the four reductions interleaved
+    float p[4][2], mx[4], ssum[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const float l0 = act0 ? kAttnScale * d[i][0] : -INFINITY, l1 = act1 ? kAttnScale * d[i][1] : -INFINITY;
-        const float m = group_max<LPR>(fmaxf(l0, l1));
-        const float e0 = act0 ? expf(l0 - m) : 0.f, e1 = act1 ? expf(l1 - m) : 0.f;
-        const float ssum = group_sum<LPR>(e0 + e1);
-        p[i][0] = e0 / ssum; p[i][1] = e1 / ssum;
+        p[i][0] = act0 ? kAttnScale * d[i][0] : -INFINITY; p[i][1] = act1 ? kAttnScale * d[i][1] : -INFINITY;
+        mx[i] = fmaxf(p[i][0], p[i][1]);
+    }
+    group_max_n<LPR, 4>(mx);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        p[i][0] = expf(p[i][0] - mx[i]); p[i][1] = expf(p[i][1] - mx[i]);
+        ssum[i] = p[i][0] + p[i][1];
+    }
+    group_sum_n<LPR, 4>(ssum);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float inv = __frcp_rn(ssum[i]);
+        p[i][0] *= inv; p[i][1] *= inv;
         const int row = rbase + i;
         if (u.valid && i >= shift && i - shift < u.cnt) {
             if (sub < NP) st_p[(size_t)row * NP + sub] = p[i][0];
             if (LPR + sub < NP) st_p[(size_t)row * NP + LPR + sub] = p[i][1];
         }
     }
+    c.mark(30);
     float o[4][DPL];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -1182,6 +1218,7 @@ __device__ __forceinline__ void attn_forward_quads(Ctx2& c, const LayerDev& W, i
             }
         }
     }
+    c.mark(31);
     c.slot_acquire();
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -1206,13 +1243,18 @@ __device__ __forceinline__ void attn_backward_ds_dq_quads(Ctx2& c, int N, int NP
     lane_dots8<AM::KPL>(c.sO + rbase * C::LDO, C::LDO, c.sQKV + (u.r0 + min(sub, N - 1)) * C::LDQ + 128,
                c.sQKV + (u.r0 + min(LPR + sub, N - 1)) * C::LDQ + 128, d);
     const bool act0 = sub < N, act1 = LPR + sub < N;
-    float ds[4][2];
+    float ds[4][2], tsum[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int row = rbase + i;
-        const float p0 = act0 ? c.sP[row * NP + sub] : 0.f, p1 = act1 ? c.sP[row * NP + LPR + sub] : 0.f;
-        const float t = group_sum<LPR>(p0 * d[i][0] + p1 * d[i][1]);
-        ds[i][0] = p0 * (d[i][0] - t); ds[i][1] = p1 * (d[i][1] - t);
+        ds[i][0] = act0 ? c.sP[row * NP + sub] : 0.f; ds[i][1] = act1 ? c.sP[row * NP + LPR + sub] : 0.f;     // p
+        tsum[i] = ds[i][0] * d[i][0] + ds[i][1] * d[i][1];
+    }
+    group_sum_n<LPR, 4>(tsum);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int row = rbase + i;
+        ds[i][0] *= d[i][0] - tsum[i]; ds[i][1] *= d[i][1] - tsum[i];
         if (u.valid && i >= shift && i - shift < u.cnt) {
             if (sub < NP) c.sDS[row * NP + sub] = ds[i][0];
             if (LPR + sub < NP) c.sDS[row * NP + LPR + sub] = ds[i][1];
@@ -1375,26 +1417,27 @@ __device__ void forward_pass_tc(const ModelDev& M, Ctx2& c, float t_norm, const 
             {   // q | k' | v' of the head chunk: TMEM -> shared (row-major, for the attention) + stash
                 const int b = c.dq_wait();
                 c.mark(1);
-                float* st_qkv = st + M.off[ST_QKV] + (size_t)hc * R * 3 * C::CWQ;
+                float* st_qkv = st + M.off[ST_QKV] + (size_t)hc * R * C::LDQ;
                 tmem_foreach<192>(c.tmem, C::kColD + b * 192, rows, [&](int row, int col, const float (&v)[16]) {
 #pragma unroll
                     for (int i = 0; i < 16; i += 4)
                         *reinterpret_cast<float4*>(c.sQKV + row * C::LDQ + col + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
                 });
+                // stash copy for the reverse pass: ONE asynchronous bulk copy (shared -> global; the stash keeps the LDQ row stride),
+                // issued after the hand-off.  It drains during the attention phase and keeps the load/store unit free:
+                // register-staged stores of these 46 KB held up every global access of the attention phase.
+                if (tid == 0) bulk_wait_read();        // p of the previous chunk has left sP
+                fence_proxy_async();
                 c.dq_release();
-                // stash copy for the reverse pass: coalesced row stores by all threads, issued after the hand-off so that
-                // they drain during the attention phase (no fence waits on them)
-                for (int idx = tid; idx < rows * 48; idx += kCT) {
-                    const int r = idx / 48, c4 = idx - r * 48;
-                    *reinterpret_cast<float4*>(st_qkv + (size_t)r * (3 * C::CWQ) + c4 * 4) = *reinterpret_cast<const float4*>(c.sQKV + r * C::LDQ + c4 * 4);
-                }
+                if (tid == 0) bulk_s2g(st_qkv, c.sQKV, (uint32_t)(rows * C::LDQ) * sizeof(float));
                 c.mark(2);
             }
             if constexpr (!C::kAttMma) {
                 // logits, softmax, P V' - A x_i + c -> canonical operand of the out-projection (row-local, no barrier inside)
-                if (c.quads) attn_forward_quads<C>(c, W, hc, N, NP, st + M.off[ST_P] + (size_t)hc * R * NP);
-                else if (c.pairs) attn_forward_pairs<C>(c, W, hc, N, NP, st + M.off[ST_P] + (size_t)hc * R * NP);
-                else attn_forward_rows<C>(c, W, hc, N, NP, st + M.off[ST_P] + (size_t)hc * R * NP);
+                // (p goes to sP; its stash copy is one bulk copy after the hand-off below)
+                if (c.quads) attn_forward_quads<C>(c, W, hc, N, NP, c.sP);
+                else if (c.pairs) attn_forward_pairs<C>(c, W, hc, N, NP, c.sP);
+                else attn_forward_rows<C>(c, W, hc, N, NP, c.sP);
             } else {
                 // logits (HMMA items) | softmax (rows) | P V' - A x_i + c (HMMA items) -> canonical operand of the out-projection
                 const AttnGeo G(N, NP, c.S_act);
@@ -1402,7 +1445,7 @@ __device__ void forward_pass_tc(const ModelDev& M, Ctx2& c, float t_norm, const 
                 attn_logits_items<C>(c.sQKV, c.sP, W.A, hc, dist, G);
                 csync();
                 c.mark(23);
-                attn_softmax_rows<C>(c.sP, st + M.off[ST_P] + (size_t)hc * R * NP, c.sQKV, c.sX, c.sO + 64, C::LDO, dist, G);     // z -> sO pad (free in the forward pass)
+                attn_softmax_rows<C>(c.sP, c.sQKV, c.sX, c.sO + 64, C::LDO, dist, G);     // z -> sO pad (free in the forward pass)
                 csync();
                 c.mark(24);
                 attn_weighted_items<C>(c.sP, c.sQKV, C::LDQ, 128, G, [&](int row, int col, float v0, float v1) {
@@ -1418,7 +1461,9 @@ __device__ void forward_pass_tc(const ModelDev& M, Ctx2& c, float t_norm, const 
                 });
             }
             c.mark(3);
+            if (tid == 0) bulk_wait_read();        // q | k' | v' have left sQKV (the copy had the whole attention phase)
             c.slot_post();
+            if (tid == 0) bulk_s2g(st + M.off[ST_P] + (size_t)hc * R * NP, c.sP, (uint32_t)(rows * NP) * sizeof(float));
             c.mark(4);
         }
         // attention block output -> row buffer; gated residual 1 + LayerNorm 2 -> canonical operand of FF1
@@ -1499,6 +1544,7 @@ __device__ void forward_pass_tc(const ModelDev& M, Ctx2& c, float t_norm, const 
         gate_ln_forward_rows_can<C>(c.sN, c.sNh, c.nhat_hi, c.nhat_lo, W.g2a, W.g2b, H, rows, st + M.off[ST_FF], st + M.off[ST_G2],
                                     stn + M.off[ST_NIN], last ? nullptr : M.layer[l + 1].ln1_g,
                                     last ? nullptr : M.layer[l + 1].ln1_b, last ? nullptr : stn + M.off[ST_STAT1]);
+        if (tid == 0) bulk_wait_read();            // the layer's last p copy has left sP
         if (!last) c.post(); else csync();
         c.mark(7);
     }
@@ -1517,6 +1563,7 @@ __device__ void backward_pass_tc(const ModelDev& M, Ctx2& c) {
         c.sN[r * C::LDH + d] = (d < H) ? __ldg(M.dec_w + d) : 0.f;      // dE_r/dn_r = w_dec  (node_decoder, :106)
     }
     for (int idx = tid; idx < R * 4; idx += kCT) c.sDX[idx] = 0.f;
+    if (tid == 0) bulk_wait_all();                 // the forward pass's bulk stash copies are complete before anything is reloaded
     csync();
 
     for (int l = M.L - 1; l >= 0; --l) {
@@ -1585,15 +1632,12 @@ __device__ void backward_pass_tc(const ModelDev& M, Ctx2& c) {
         c.mark(14);
 
         for (int hc = 0; hc < C::NCH; ++hc) {
-            // start reloading q | k' | v' and p of this chunk; the copies land while d o is read back
-            {
-                const float* src = st + M.off[ST_QKV] + (size_t)hc * R * 3 * C::CWQ;
-                for (int idx = tid; idx < rows * 48; idx += kCT) {
-                    const int r = idx / 48, c4 = idx - r * 48;
-                    cp_async16(c.sQKV + r * C::LDQ + c4 * 4, src + (size_t)r * 192 + c4 * 4);
-                }
-                const float* srcp = st + M.off[ST_P] + (size_t)hc * R * NP;
-                for (int idx = tid; idx < (rows * NP) / 4; idx += kCT) cp_async16(c.sP + idx * 4, srcp + idx * 4);
+            // start reloading q | k' | v' and p of this chunk (two bulk copies onto one mbarrier); they land while d o is read back
+            if (tid == 0) {
+                const uint32_t bq = (uint32_t)(rows * C::LDQ) * sizeof(float), bp = (uint32_t)(rows * NP) * sizeof(float);
+                mbar_expect_tx(c.bars + B_RELOAD, bq + bp);
+                bulk_g2s(c.sQKV, st + M.off[ST_QKV] + (size_t)hc * R * C::LDQ, bq, c.bars + B_RELOAD);
+                bulk_g2s(c.sP, st + M.off[ST_P] + (size_t)hc * R * NP, bp, c.bars + B_RELOAD);
             }
             {   // d o_chunk = d att x Wo_b[l][hc]: TMEM -> shared
                 c.mark(15);
@@ -1604,7 +1648,8 @@ __device__ void backward_pass_tc(const ModelDev& M, Ctx2& c) {
                     for (int i = 0; i < 16; i += 4)
                         *reinterpret_cast<float4*>(c.sO + row * C::LDO + col + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
                 });
-                cp_async_wait_all();
+                mbar_wait_wd(c.bars + B_RELOAD, c.n_reload & 1u, 9);
+                ++c.n_reload;
                 c.dq_release();
                 c.mark(16);
             }
@@ -1742,7 +1787,7 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
     if (tid == 0) {
         for (int i = 0; i < C::kStages; ++i) { mbar_init(bars + B_FULL + i, 1); mbar_init(bars + B_EMPTY + i, 1); }
         mbar_init(bars + B_DQ, 1); mbar_init(bars + B_DQ + 1, 1);
-        mbar_init(bars + B_ACC, 1); mbar_init(bars + B_D1, 1); mbar_init(bars + B_SLOT, 1);
+        mbar_init(bars + B_ACC, 1); mbar_init(bars + B_D1, 1); mbar_init(bars + B_SLOT, 1); mbar_init(bars + B_RELOAD, 1);
         for (int i = 0; i < 8; ++i) mbar_init(bars + B_POST + i, 1);
         mbar_init(bars + B_DRAIN, 1); mbar_init(bars + B_DRAIN + 1, 1);
         fence_barrier_init();
@@ -1767,8 +1812,13 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
                     for (uint32_t s = 0; s < jb.n_slices; ++s, ++slice_i) {
                         const uint32_t stg = slice_i % C::kStages, use = slice_i / C::kStages;
                         { TCP_BEGIN(); if (use > 0) mbar_wait_wd(bars + B_EMPTY + stg, (use - 1) & 1u, 5); TCP_END(pw, 0); }
-                        mbar_expect_tx(bars + B_FULL + stg, slice_bytes);
-                        bulk_g2s(smem + C::oW + stg * C::kStageFloats, src + (size_t)s * slice_bytes, slice_bytes, bars + B_FULL + stg);
+#ifdef DFF_EXP_STREAM_DIV      // timing experiment only (wrong results): stream a fraction of every weight slice
+                        const uint32_t cp_bytes = max(16u, (slice_bytes / DFF_EXP_STREAM_DIV) & ~15u);
+#else
+                        const uint32_t cp_bytes = slice_bytes;
+#endif
+                        mbar_expect_tx(bars + B_FULL + stg, cp_bytes);
+                        bulk_g2s(smem + C::oW + stg * C::kStageFloats, src + (size_t)s * slice_bytes, cp_bytes, bars + B_FULL + stg);
                     }
                 }
             (void)nslices;
@@ -1829,19 +1879,27 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
                         uint64_t dbl = dbh + lo_off;
                         { TCP_BEGIN(); mbar_wait_wd(bars + B_FULL + stg, use & 1u, 6); TCP_END(iw, 2); }
                         tc::fence_after_sync();
+#ifdef DFF_EXP_ONE_PASS        // timing experiment only (TF32-grade results): hi*hi alone, a third of the MMAs
+                        if (tc::elect_one()) tc::mma_tf32_ss(d_tmem, dah, dbh, idesc, acc);
+#else
                         if (tc::elect_one()) {
                             tc::mma_tf32_ss(c_tmem, dal, dbh, idesc, acc);          // first k-step of the slice (may overwrite D)
                             tc::mma_tf32_acc(c_tmem, dah, dbl, idesc);
                             tc::mma_tf32_ss(d_tmem, dah, dbh, idesc, split ? acc : 1u);
                         }
+#endif
                         acc = 1u;
                         for (uint32_t kk = 1; kk < ksteps; ++kk) {
                             dah += a_step; dal += a_step; dbh += b_step; dbl += b_step;
+#ifdef DFF_EXP_ONE_PASS
+                            if (tc::elect_one()) tc::mma_tf32_acc(d_tmem, dah, dbh, idesc);
+#else
                             if (tc::elect_one()) {
                                 tc::mma_tf32_acc(c_tmem, dal, dbh, idesc);
                                 tc::mma_tf32_acc(c_tmem, dah, dbl, idesc);
                                 tc::mma_tf32_acc(d_tmem, dah, dbh, idesc);
                             }
+#endif
                         }
                         dah += a_step; dal += a_step;
                         if (tc::elect_one()) tc::commit(bars + B_EMPTY + stg);
@@ -1870,7 +1928,7 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
         c.sDX = smem + C::oDX; c.sTmp = smem + C::oTmp;
         c.nhat_hi = smem + C::oNhatHi; c.nhat_lo = smem + C::oNhatLo; c.slot_hi = smem + C::oSlotHi; c.slot_lo = smem + C::oSlotLo;
         c.bars = bars; c.tmem = tmem;
-        c.n_post = c.n_drain = c.n_acc = c.n_d1 = c.n_slot = 0; c.slot_held = false;
+        c.n_post = c.n_drain = c.n_acc = c.n_d1 = c.n_slot = c.n_reload = 0; c.slot_held = false;
         for (int i = 0; i < 8; ++i) c.tw[i] = 0;
         const long long t_begin = clock64();
 #ifdef DFF_TC_PROFILE
