@@ -167,7 +167,7 @@ int launch_tc(dff_model* m, int PN, int HP, int R, int ATT, const ModelDev& M, c
                 grid, A.n_steps, s[7], s[0], s[1], s[2], s[3], s[12], s[9], s[10], s[11], s[8]);
         static const char* names[32] = {"f.init+ln", "dq_wait", "f.qkv_epi", "f.attn", "f.slot_post", "acc_wait", "f.acc_epi", "f.gate+post", "d1_wait", "f.d1copy",
                                         "f.gelu", "b.gate2+post", "b.d1copy", "b.gelu'", "b.accepi+gate1+post", "b.reload_issue", "b.do_epi", "b.ds", "b.dq+post",
-                                        "b.dk+post", "b.dv+post", "b.acc+lnbwd", "integrator", "f.logits", "f.softmax", "b.dp_uw", "b.dx", "b.dk'", "fq.pre", "fq.dots", "fq.softmax", "fq.pv"};
+                                        "b.dk+post", "b.dv+post", "b.acc+lnbwd", "integrator", "f.logits|bq.dots", "f.softmax|bq.ds", "b.dp_uw|bq.dq", "b.dx|bq.dkvloop", "b.dk'|bq.dkstore", "fq.pre", "fq.dots", "fq.softmax", "fq.pv"};
         fprintf(stderr, "[tc phases, CTA 0, cycles per step]");
         for (int i = 0; i < 32; ++i) fprintf(stderr, " %s %.0f |", names[i], (double)h[(size_t)grid * 16 + i] / A.n_steps);
         fprintf(stderr, "\n");

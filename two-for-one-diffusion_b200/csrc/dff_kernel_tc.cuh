@@ -40,7 +40,16 @@ constexpr int kMmaM = 64;                 // MMA M; a configuration uses kR <= k
 constexpr int kCW = DFF_TC_COMPUTE_WARPS;          // compute warps (multiple of 4: TMEM lane quarters)
 constexpr int kCT = kCW * 32;                      // compute threads
 constexpr int kComputeThreads = kCT;
-constexpr int kTcThreads = kComputeThreads + 64;   // + TMA producer warp + MMA issuer warp
+// + one service warpgroup: TMA producer warp, MMA issuer warp and two idle warps.  Registers are allocated to a CTA per
+// four warps (measured: a 576-thread CTA cannot launch above 96 registers), so the idle pair costs nothing, and a complete
+// warpgroup is what `setmaxnreg` needs: the service warpgroup shrinks from the launch allocation of 96 registers per thread
+// to 32 and the 16 compute warps grow to 112 (4 x 64 released = 16 x 16 acquired; ptxas schedules the compute phases with
+// the larger budget).  Measured against the 96-register build: C2 +8.6 %, C3 +4.4 %, C4 +8.5 %, C5 +3.7 %.
+#ifndef DFF_TC_SETMAXNREG
+#define DFF_TC_SETMAXNREG 1
+#endif
+constexpr int kTcThreads = kComputeThreads + (DFF_TC_SETMAXNREG ? 128 : 64);
+constexpr int kRegsCompute = 112, kRegsService = 32;
 constexpr int kTcStages = 3;
 constexpr int kJobCap = 200;              // job-table entries (16 B each) cached in shared memory
 constexpr int B_COUNT_ = 26;              // uint64 slots of the barrier block (== B_COUNT below)
@@ -149,10 +158,17 @@ __device__ __forceinline__ void csync() { asm volatile("bar.sync 1, %0;" ::"n"(k
 // (profiles/r02/README.md): a 0.2 ms hint (NANOSLEEP.SYNCS) removes the service warps' polling instructions (a third of all
 // instructions executed) but wakes later -- no gain on chignolin, -5 % on trp-cage, whose weight stream lives on wake-up latency.
 constexpr uint32_t kSpinLimit = 1u << 27;
+// The default build traps without a message: an out-of-line printf makes every wait a call site, and ptxas then spills
+// the caller's live registers around each of the ~250 waits of a step (96-188 bytes of spill traffic per wait in the
+// 96-register build, zero without the call).  -DDFF_TC_WATCHDOG_PRINTF names the wait that timed out.
+#ifdef DFF_TC_WATCHDOG_PRINTF
 static __device__ __noinline__ void watchdog_fail(int tag) {
     printf("dff_fused_tc_kernel watchdog: wait %d never completed (block %d, thread %d)\n", tag, (int)blockIdx.x, (int)threadIdx.x);
     __trap();
 }
+#else
+static __device__ __forceinline__ void watchdog_fail(int) { __trap(); }
+#endif
 __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -515,16 +531,22 @@ namespace dff {
 namespace v2 {
 
 // ------------------------------------------------------------------ row-local attention (a group of LPR lanes owns one node row)
-// LPR = 16 lanes per row for N <= 16 beads (two rows per warp), 32 for N <= 32.  Inside a group the lane index is the key
+// LPR = 16 lanes per row for N <= 16 beads (two rows per warp), 32 above.  Inside a group the lane index is the key
 // index j while logits / probabilities are formed and the output-column group (DPL = 64 / LPR columns) while values are
 // accumulated, so logits -> softmax -> P V' (forward) and dp -> ds -> dq (reverse) need no CTA-wide barrier in between
-// and all 8 warps work on every chunk even when the CTA holds only two samples.
+// and all compute warps work on every chunk even when the CTA holds only two samples.
 template <class C>
 struct AttnMap {
-    static constexpr int LPR = (C::kPN <= 16) ? 16 : 32;
+    // Largest padded N that uses 16-lane groups.  32 (two keys per lane for N in 17..32: half the shared-memory wavefronts
+    // per FMA, but half as many busy warps) was measured on trp-cage: 464 -> 399 MD steps/s -- these phases live on
+    // thread-level parallelism, not on shared-memory bandwidth.
+#ifndef DFF_TC_LPR16_MAX
+#define DFF_TC_LPR16_MAX 16
+#endif
+    static constexpr int LPR = (C::kPN <= DFF_TC_LPR16_MAX) ? 16 : 32;
     static constexpr int DPL = 64 / LPR;
     static constexpr int UPW = 32 / LPR;              // rows per warp and round
-    static constexpr int KPL = (C::kPN > 32) ? 2 : 1; // keys per lane (N > 32: lane j also owns key j + 32; pair-local routines only)
+    static constexpr int KPL = (C::kPN > LPR) ? 2 : 1; // keys per lane (lane j also owns key j + LPR; pair- / quad-local routines only)
 };
 template <int LPR>
 __device__ __forceinline__ float group_sum(float v) {
@@ -1242,6 +1264,7 @@ __device__ __forceinline__ void attn_backward_ds_dq_quads(Ctx2& c, int N, int NP
     float d[4][2];
     lane_dots8<AM::KPL>(c.sO + rbase * C::LDO, C::LDO, c.sQKV + (u.r0 + min(sub, N - 1)) * C::LDQ + 128,
                c.sQKV + (u.r0 + min(LPR + sub, N - 1)) * C::LDQ + 128, d);
+    c.mark(23);
     const bool act0 = sub < N, act1 = LPR + sub < N;
     float ds[4][2], tsum[4];
 #pragma unroll
@@ -1260,6 +1283,7 @@ __device__ __forceinline__ void attn_backward_ds_dq_quads(Ctx2& c, int N, int NP
             if (LPR + sub < NP) c.sDS[row * NP + LPR + sub] = ds[i][1];
         }
     }
+    c.mark(24);
     if (want_dq) {
         float q[4][DPL];
 #pragma unroll
@@ -1281,6 +1305,7 @@ __device__ __forceinline__ void attn_backward_ds_dq_quads(Ctx2& c, int N, int NP
                 }
             }
         }
+        c.mark(25);
         c.slot_acquire();
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -1337,6 +1362,7 @@ __device__ __forceinline__ void attn_backward_dkv_quads(Ctx2& c, const LayerDev&
 #pragma unroll
             for (int e = 0; e < DPL; ++e) dk[h][e] *= kAttnScale;
     }
+    c.mark(26);
     if (to_slot) {          // job d k'
         c.slot_acquire();
 #pragma unroll
@@ -1344,6 +1370,7 @@ __device__ __forceinline__ void attn_backward_dkv_quads(Ctx2& c, const LayerDev&
             if (h < cnt) can_store_group<DPL, C::kCS>(c.slot_hi, c.slot_lo, r0 + j0 + h, sub, dk[h]);
         c.slot_post();
     }
+    c.mark(27);
     // dx_j += A_h^T (dk'_j + dv'_j - do_j): runs while the tensor core consumes d k'
     {
         float g[4][3];
@@ -1757,7 +1784,11 @@ __device__ void backward_pass_tc(const ModelDev& M, Ctx2& c) {
 
 // ------------------------------------------------------------------ the kernel
 template <class C>
+#ifdef DFF_TC_MAXNREG
+__global__ void __maxnreg__(DFF_TC_MAXNREG)
+#else
 __global__ void __launch_bounds__(kTcThreads, 1)
+#endif
 dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ StepArgs A, const __grid_constant__ TcArgs T) {
     constexpr int R = C::kR;
     extern __shared__ __align__(128) float smem[];
@@ -1799,7 +1830,19 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
     tc::fence_after_sync();
     const uint32_t tmem = ctr[0];
 
+#if DFF_TC_SETMAXNREG
+#define DFF_REG_DEC() asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsService))
+#define DFF_REG_INC() asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsCompute))
+#else
+#define DFF_REG_DEC() do { } while (0)
+#define DFF_REG_INC() do { } while (0)
+#endif
+    // Every warp of the service warpgroup shrinks at the top of its own role branch (same register count; the pattern of the
+    // CUTLASS sm100 role-specialised kernels).  One shared setmaxnreg ahead of the role dispatch compiles to code that is no
+    // faster than the 96-register build (measured on one box: 3254 vs 3559 MD steps/s on C2, 464 vs 509 on C4).
+    if (warp >= kCW) {
     if (warp == kComputeThreads / 32) {
+        DFF_REG_DEC();
         // ===================================================== TMA producer: streams the weight slices of every job
         if ((tid & 31) == 0) {
             uint32_t slice_i = 0;
@@ -1827,6 +1870,7 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
 #endif
         }
     } else if (warp == kComputeThreads / 32 + 1) {
+        DFF_REG_DEC();
         // ===================================================== MMA issuer: walks the job table.
         // The whole warp runs the (warp-uniform) control flow and descriptor arithmetic, so that the operands of
         // tcgen05.mma stay in uniform registers; one elected lane issues the MMAs and commits.
@@ -1921,7 +1965,11 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
 #endif
         }
     } else {
+        DFF_REG_DEC();        // (DFF_TC_SETMAXNREG: warps kCW + 2, kCW + 3 idle)
+    }
+    } else {
         // ===================================================== compute warps
+        DFF_REG_INC();
         Ctx2 c;
         c.sQKV = smem + C::oQKV; c.sNh = c.sQKV; c.sO = smem + C::oO;
         c.sP = smem + C::oP; c.sDS = smem + C::oDS; c.sX = smem + C::oX; c.sV = smem + C::oV;
@@ -1949,9 +1997,9 @@ dff_fused_tc_kernel(const __grid_constant__ ModelDev M, const __grid_constant__ 
 #ifndef DFF_TC_QUADS16
 #define DFF_TC_QUADS16 0
 #endif
-            c.quads = (AttnMap<C>::LPR == 32 || DFF_TC_QUADS16) && c.rows_act > kCW * AttnMap<C>::UPW && N >= 4 &&
+            c.quads = (AttnMap<C>::LPR == 32 || AttnMap<C>::KPL == 2 || DFF_TC_QUADS16) && c.rows_act > kCW * AttnMap<C>::UPW && N >= 4 &&
                       c.S_act * ((N + 3) >> 2) <= kCW * AttnMap<C>::UPW;      // more rows than lane groups, one quad per group
-            c.pairs = c.rows_act > kCW * AttnMap<C>::UPW;
+            c.pairs = c.rows_act > kCW * AttnMap<C>::UPW || AttnMap<C>::KPL == 2;      // (the row-local routines hold one key per lane)
             for (int idx = tid; idx < R * 3; idx += kCT) {
                 const int r = idx / 3, cc = idx - r * 3;
                 const bool ok = r < c.rows_act;
