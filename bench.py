@@ -476,7 +476,8 @@ def main():
 
     rl = roofline(hb, a.workload, r["dev_ms"], units_rank)
     cfg_used = hb.eng.last_config
-    kernel = ("dff_fused_tc_kernel (tcgen05.mma kind::tf32 projections with TMEM accumulators; mma.sync tf32 attention tiles)"
+    kernel = ("dff_fused_tc_kernel (tcgen05.mma kind::tf32 projections with TMEM accumulators, TMA bulk copies for weights and stash; "
+              "fp32 SIMT attention contractions)"
               if cfg_used == "tc" else f"dff_fused_kernel ({cfg_used}; mma.sync tf32)")
     rl.update({"kernel": kernel, "flops_per_launch": hb.flops_per_sample * B * per_step,
                "note": "collapsed-formulation FLOPs (SURVEY 8d) per launch / CUDA-event time. The tcgen05 projections run kind::tf32 (half the "

@@ -110,7 +110,11 @@ struct TcCfg {
     static constexpr bool kNodeInSmem = (kHP == 64);
     // weight ring depth = what fits next to the row buffers: hidden 64 (16 KB stages): 3 (4 with 60-row buffers), 2 for N > 32; hidden 96 / 128
     // (12 KB stages): 4 when the pass has fewer than 64 rows (smaller row buffers), else 3
+#ifdef DFF_EXP_STAGES
+    static constexpr int kStages = DFF_EXP_STAGES;
+#else
     static constexpr int kStages = (HP_ == 64) ? (PN_ > 32 ? 2 : (R_ < 64 && PN_ <= 12 ? 4 : 3)) : (R_ < 64 ? 4 : 3);
+#endif
     static constexpr int kStageFloats = (kHP == 64) ? 4096 : 3072;
     static constexpr uint32_t kColD = kHP;                   // TMEM work area
     // Correction accumulators (DFF_TC_SPLIT_ACC): the two small split-precision products of a long K chain accumulate
