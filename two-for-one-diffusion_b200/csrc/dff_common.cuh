@@ -125,6 +125,14 @@ __device__ __forceinline__ void bulk_wait_all() {                               
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     asm volatile("fence.proxy.async;" ::: "memory");
 }
+// Drop the L2 lines that lie completely inside [p, p + bytes) without writing them back (PTX discard.global.L2): for scratch
+// data that has been consumed and will be rewritten before it is read again.  Strided over `nthreads` callers.
+__device__ __forceinline__ void discard_l2_range(const void* p, size_t bytes, int tid, int nthreads) {
+    const unsigned long long lo = (reinterpret_cast<unsigned long long>(p) + 127ull) & ~127ull;
+    const unsigned long long hi = (reinterpret_cast<unsigned long long>(p) + bytes) & ~127ull;
+    for (unsigned long long a = lo + (unsigned long long)tid * 128ull; a < hi; a += (unsigned long long)nthreads * 128ull)
+        asm volatile("discard.global.L2 [%0], 128;" ::"l"(a) : "memory");
+}
 __device__ __forceinline__ void fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
