@@ -252,7 +252,7 @@ __device__ __forceinline__ void attn_softmax_rows(float* sP, const float* sQKV, 
         float m = fmaxf(l0, l1);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        const float e0 = a0 ? expf(l0 - m) : 0.f, e1 = a1 ? expf(l1 - m) : 0.f;
+        const float e0 = a0 ? fast_exp(l0 - m) : 0.f, e1 = a1 ? fast_exp(l1 - m) : 0.f;
         const float inv = 1.0f / warp_sum(e0 + e1);
         const float p0 = e0 * inv, p1 = e1 * inv;
         if (lane < G.NP) row[lane] = p0;              // (the caller copies sP to the stash)
