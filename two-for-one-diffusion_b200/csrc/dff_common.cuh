@@ -140,7 +140,7 @@ __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-// 16-byte Ampere-style async copy global -> shared (SASS: LDGSTS), used for the stash reloads
+// 16-byte Ampere-style async copy global -> shared (SASS: LDGSTS), used for the stash reloads of the mma.sync kernel
 __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
 }

@@ -9,12 +9,14 @@
 //   * fp32-grade accuracy = 3xTF32 split precision: activations are written by their producers directly in the
 //     UMMA canonical K-major layout as a TF32-exact high part and a low part, the weights are pre-split on the
 //     host; lo*hi + hi*lo + hi*hi accumulate in the fp32 TMEM accumulator;
-//   * weights arrive as pre-split, pre-laid-out [hi | lo] slices through a 2/3-stage ring filled by a dedicated
+//   * weights arrive as pre-split, pre-laid-out [hi | lo] slices through a 2-4-stage ring filled by a dedicated
 //     TMA producer thread (cp.async.bulk + mbarrier expect_tx) and released by `tcgen05.commit`;
 //   * the CTA is warp-specialised: 16 compute warps (attention, softmax, LayerNorm, gates, GELU, integrators,
-//     TMEM epilogues) + 1 TMA producer warp + 1 MMA issuer warp.  The issuer follows a host-built job table, so
+//     TMEM epilogues) + a service warpgroup (TMA producer warp, MMA issuer warp, two idle warps) that hands its registers
+//     to the compute warps with setmaxnreg (96 -> 32 / 112).  The issuer follows a host-built job table, so
 //     the QKV projection of head chunk h+1 and the out-projection of chunk h-1 run on the tensor core WHILE the
 //     compute warps do the attention of chunk h (double-buffered TMEM accumulators);
+//   * the two big stash pieces (q|k'|v' and p of a head chunk) leave and re-enter shared memory as TMA bulk copies;
 //   * the folded edge term  A x_j  and the q/k/v biases ride inside the QKV GEMM as 8 extra K rows
 //     (operand row = [n_hat | x0 x1 x2 1 0 0 0 0]), so that epilogue is a pure TMEM -> smem/stash copy.
 //
